@@ -1,0 +1,102 @@
+// comm.h — fragment-group communicator and the per-app message manager.
+//
+// Replaces grape::cuda::GPUMessageManager + dev::MessageManager +
+// dev::InArchive/OutArchive (grape/cuda/parallel/gpu_message_manager.h:45-458,
+// grape/cuda/serialization/in_archive.h:36-169, out_archive.h:32-178).
+//
+// B200 design: no host-side size exchange and no NCCL send/recv of byte
+// archives.  Every rank owns ONE device allocation ("landing area") that its
+// peers map through CUDA IPC; a producer kernel writes (lid_at_owner, value)
+// items straight into the owner's landing slot over NVLink (peer stores) and
+// then publishes the item count.  Slots are double-buffered by round parity so
+// that round r+1 producers never overwrite round r items still being applied.
+// The only host step per round is one tiny all-reduce that is both the
+// barrier and the termination vote (gpu_message_manager.h:400-431 does an
+// MPI_Allgather of sizes + MPI_Barrier for the same purpose).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+constexpr uint32_t GL_MAX_FNUM = 64;
+constexpr size_t GL_COMM_HEADER = 4096;  // counts[2][GL_MAX_FNUM] u32 + flags
+
+struct gl_comm {
+  uint32_t fid = 0, fnum = 1;
+  gl_allreduce_fn allreduce = nullptr;
+  void* user = nullptr;
+  size_t landing_bytes = 0;  // per (parity, src) slot
+  char* local_base = nullptr;
+  std::vector<char*> peer_base;  // [fnum]; peer_base[fid] == local_base
+  bool opened = false;
+  size_t total_bytes() const {
+    return GL_COMM_HEADER + 2 * (size_t) fnum * landing_bytes;
+  }
+};
+
+namespace gl {
+
+// Device-side view handed to producer / consumer kernels.
+struct MsgView {
+  uint32_t fid, fnum;
+  int fid_offset;
+  uint32_t id_mask;
+  uint32_t item_bytes;
+  uint32_t capacity;        // items per slot
+  char* const* send_slot;   // device table [fnum]: peer landing slot for (parity, me)
+  uint32_t* send_count;     // device [fnum] local counters
+  const char* const* recv_slot;  // device table [fnum]: my landing slot for (prev parity, src)
+  const uint32_t* recv_count;    // device [fnum] (inside my header, prev parity)
+};
+
+struct MessageManager {
+  gl_comm* comm = nullptr;
+  uint32_t fid = 0, fnum = 1;
+  int fid_offset = 31;
+  uint32_t id_mask = 0x7fffffffu;
+  uint32_t item_bytes = 8;
+  int round = 0;
+  bool force_continue = false;
+  bool terminate = false;
+  uint64_t bytes_sent = 0;
+  // device tables
+  char** d_send_slot[2] = {nullptr, nullptr};        // [parity][fnum]
+  const char** d_recv_slot[2] = {nullptr, nullptr};  // [parity][fnum]
+  uint32_t* d_send_count = nullptr;                  // [fnum]
+  uint32_t* h_send_count = nullptr;                  // pinned [fnum+1]
+  uint32_t** d_peer_count[2] = {nullptr, nullptr};   // [parity][fnum] address of my count cell at peer
+
+  int Init(gl_comm* c, const gl_frag_view& fv, uint32_t item_bytes_);
+  void Destroy();
+  // GPUMessageManager::StartARound / FinishARound / ToTerminate / ForceContinue
+  void Start() { round = 0; force_continue = false; terminate = false; bytes_sent = 0; }
+  int StartARound(cudaStream_t s);
+  int FinishARound(cudaStream_t s);
+  bool ToTerminate() const { return terminate; }
+  void ForceContinue() { force_continue = true; }
+  // view for producers of the current round and consumers of the previous one
+  MsgView view() const;
+  // all-reduce helpers (cuda::Communicator::Sum/Min/Max, communicator.h:41-84)
+  int AllReduceI64(int64_t* v, int n, int op);
+  int AllReduceF64(double* v, int n, int op);
+};
+
+#ifdef __CUDACC__
+// append one item to the slot of fragment `dst` (warp-aggregated per
+// destination; replaces dev::InArchive::AddBytesWarpOpt, in_archive.h:51-67)
+template <typename Item>
+GL_DEV void msg_send(const MsgView& mv, bool pred, uint32_t dst, const Item& it) {
+  // group lanes by destination
+  uint32_t active = __ballot_sync(0xffffffffu, pred);
+  if (!pred) return;
+  uint32_t peers = __match_any_sync(active, dst);
+  uint32_t leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (lane_id() == leader) base = atomicAdd(mv.send_count + dst, __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  uint32_t pos = base + __popc(peers & ((1u << lane_id()) - 1));
+  if (pos < mv.capacity) ((Item*) mv.send_slot[dst])[pos] = it;
+}
+#endif
+
+}  // namespace gl

@@ -1,0 +1,259 @@
+// primitives.cu — C-ABI engine primitives: fixed-function ForEachOutgoingEdge
+// over a WorkSourceArray with the reference's load-balancing modes
+// (grape/cuda/parallel/parallel_engine.h:987-1013, 1184-1394) and bitmap
+// compaction (the ForEach+AppendWarp idiom, cuda/sssp/sssp.h:223-232).
+#include <cub/cub.cuh>
+
+#include "apps_common.cuh"
+
+namespace gl {
+namespace {
+
+struct OpLevel {
+  using Meta = uint32_t;
+  using W = float;
+  static constexpr bool kWeighted = false;
+  uint32_t* level;
+  uint32_t* out;
+  uint32_t depth;
+  GL_DEV Meta assign(uint32_t) const { return 0; }
+  GL_DEV void edge(uint32_t, Meta, uint32_t v, W, ScanAcc& acc) const {
+    if (level[v] == kInfU32) {
+      if (atomicCAS(level + v, kInfU32, depth) == kInfU32) {
+        if (out) bit_set_atomic(out, v);
+        acc.next_count++;
+      }
+    }
+  }
+};
+struct OpMinU32 {
+  using Meta = uint32_t;
+  using W = float;
+  static constexpr bool kWeighted = true;
+  uint32_t* state;
+  uint32_t* out;
+  int use_w;
+  GL_DEV Meta assign(uint32_t u) const { return state[u]; }
+  GL_DEV void edge(uint32_t, Meta m, uint32_t v, W w, ScanAcc& acc) const {
+    uint32_t nv = use_w ? m + (uint32_t) w : m;
+    if (nv < atomicMin(state + v, nv)) {
+      if (out) bit_set_atomic(out, v);
+      acc.next_count++;
+    }
+  }
+};
+struct OpMinF32 {
+  using Meta = float;
+  using W = float;
+  static constexpr bool kWeighted = true;
+  float* state;
+  uint32_t* out;
+  int use_w;
+  GL_DEV Meta assign(uint32_t u) const { return state[u]; }
+  GL_DEV void edge(uint32_t, Meta m, uint32_t v, W w, ScanAcc& acc) const {
+    float nv = use_w ? m + w : m;
+    if (nv < atomic_min_f32_nonneg(state + v, nv)) {
+      if (out) bit_set_atomic(out, v);
+      acc.next_count++;
+    }
+  }
+};
+struct OpAddF64 {
+  using Meta = double;
+  using W = float;
+  static constexpr bool kWeighted = false;
+  const double* src;
+  double* dst;
+  GL_DEV Meta assign(uint32_t u) const { return src[u]; }
+  GL_DEV void edge(uint32_t, Meta m, uint32_t v, W, ScanAcc&) const {
+    atomicAdd(dst + v, m);
+  }
+};
+struct OpCount {
+  using Meta = uint32_t;
+  using W = float;
+  static constexpr bool kWeighted = false;
+  unsigned long long* sink;
+  GL_DEV Meta assign(uint32_t) const { return 0; }
+  GL_DEV void edge(uint32_t, Meta, uint32_t v, W, ScanAcc& acc) const {
+    acc.aux += (v == 0xFFFFFFFEu);  // keeps the column load alive
+  }
+};
+
+struct PrimScratch {
+  ScanCtrl* ctrl = nullptr;
+  ScanCtrl* h_ctrl = nullptr;
+  HubItem* hubs = nullptr;
+  uint32_t hub_cap = 0;
+  uint64_t* deg = nullptr;
+  uint64_t* pfx = nullptr;
+  uint32_t pfx_cap = 0;
+  void* scan_tmp = nullptr;
+  size_t scan_bytes = 0;
+};
+thread_local PrimScratch g_ps;
+
+int ensure_scratch(const gl_frag* f, uint32_t n) {
+  PrimScratch& ps = g_ps;
+  if (!ps.ctrl) {
+    GL_CUDA(cudaMalloc(&ps.ctrl, sizeof(ScanCtrl)));
+    GL_CUDA(cudaMallocHost(&ps.h_ctrl, sizeof(ScanCtrl)));
+  }
+  uint64_t m = std::max<uint64_t>(f->oe.entries, 1);
+  uint32_t need = (uint32_t) std::min<uint64_t>(m / kHubChunk + m / kHubDeg + 1024, 0x7FFFFFFFull);
+  if (need > ps.hub_cap) {
+    if (ps.hubs) cudaFree(ps.hubs);
+    GL_CUDA(cudaMalloc(&ps.hubs, sizeof(HubItem) * (size_t) need));
+    ps.hub_cap = need;
+  }
+  if (n + 1 > ps.pfx_cap) {
+    if (ps.deg) cudaFree(ps.deg);
+    if (ps.pfx) cudaFree(ps.pfx);
+    if (ps.scan_tmp) cudaFree(ps.scan_tmp);
+    GL_CUDA(cudaMalloc(&ps.deg, sizeof(uint64_t) * ((size_t) n + 1)));
+    GL_CUDA(cudaMalloc(&ps.pfx, sizeof(uint64_t) * ((size_t) n + 1)));
+    ps.scan_bytes = 0;
+    GL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, ps.scan_bytes, ps.deg, ps.pfx, (int) (n + 1)));
+    GL_CUDA(cudaMalloc(&ps.scan_tmp, ps.scan_bytes));
+    ps.pfx_cap = n + 1;
+  }
+  return GL_OK;
+}
+
+template <class Op>
+int scan_queue(const gl_frag* f, cudaStream_t s, const uint32_t* q, uint32_t n,
+               const Op& op, int lb, uint64_t* scanned_host) {
+  GL_TRY(ensure_scratch(f, n));
+  PrimScratch& ps = g_ps;
+  DeviceInfo* di;
+  GL_TRY(device_info(&di));
+  EdgeRange er{f->oe.rp, f->oe.col, f->oe.w};
+  GL_CUDA(cudaMemsetAsync(ps.ctrl, 0, sizeof(ScanCtrl), s));
+  if (n) {
+    switch (lb) {
+      case GL_LB_NONE: {
+        int g = std::min<int>(persistent_grid(k_queue_scan_none<Op>, di->sm_count), (int) ((n + kTB - 1) / kTB));
+        GL_LAUNCH(k_queue_scan_none<Op>, g, kTB, s, q, n, er, op, ps.ctrl);
+        break;
+      }
+      case GL_LB_WM: {
+        int g = std::min<int>(persistent_grid(k_queue_scan_warp<Op>, di->sm_count), (int) ((n + kTB - 1) / kTB));
+        GL_LAUNCH(k_queue_scan_warp<Op>, g, kTB, s, q, n, er, op, ps.ctrl);
+        break;
+      }
+      case GL_LB_CM:
+      case GL_LB_CMOLD:
+      case GL_LB_CTA: {
+        // cm keeps every row inside its CTA tile; cta cuts long rows into
+        // grid-wide work items (k_hub_scan)
+        uint32_t hub_deg = lb == GL_LB_CTA ? kHubDeg : 0xFFFFFFFFu;
+        int g = std::min<int>(persistent_grid(k_queue_scan_cta<Op>, di->sm_count), (int) ((n + kTileV - 1) / kTileV));
+        GL_LAUNCH(k_queue_scan_cta<Op>, g, kTB, s, q, n, er, op, ps.ctrl, ps.hubs, ps.hub_cap, hub_deg);
+        if (lb == GL_LB_CTA) {
+          int g2 = persistent_grid(k_hub_scan<Op>, di->sm_count);
+          GL_LAUNCH(k_hub_scan<Op>, g2, kTB, s, er, op, ps.ctrl, ps.hubs, ps.hub_cap);
+        }
+        break;
+      }
+      case GL_LB_STRICT: {
+        GL_LAUNCH(k_queue_degrees, (n + 1 + 255) / 256, 256, s, q, n, f->oe.rp, ps.deg);
+        GL_CUDA(cub::DeviceScan::ExclusiveSum(ps.scan_tmp, ps.scan_bytes, ps.deg, ps.pfx, (int) (n + 1), s));
+        int g = persistent_grid(k_queue_scan_strict<Op>, di->sm_count);
+        GL_LAUNCH(k_queue_scan_strict<Op>, g, kTB, s, q, n, ps.pfx, er, op, ps.ctrl);
+        break;
+      }
+      default:
+        set_error("unknown load-balancing mode %d", lb);
+        return GL_ERR_ARG;
+    }
+  }
+  if (scanned_host) {
+    GL_CUDA(cudaMemcpyAsync(ps.h_ctrl, ps.ctrl, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, s));
+    GL_CUDA(cudaStreamSynchronize(s));
+    *scanned_host = ps.h_ctrl->scanned;
+  }
+  return GL_OK;
+}
+
+__global__ void k_compact(const uint32_t* bm, uint32_t nbits, uint32_t* q,
+                          uint32_t* count) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (nbits + stride - 1) / stride;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t r = 0; r < rounds; ++r, i += stride) {
+    bool p = i < nbits && bit_test(bm, i);
+    queue_append_warp(q, count, p, i);
+  }
+}
+
+}  // namespace
+}  // namespace gl
+
+using namespace gl;
+
+extern "C" {
+
+int gl_edge_scan_queue(const gl_frag_t* f, void* stream, const uint32_t* queue,
+                       uint32_t n, const gl_edge_op* op, int lb,
+                       uint64_t* entries_scanned_host) {
+  GL_ARG(f && op, "null argument");
+  GL_ARG(n == 0 || queue, "null queue");
+  if (f->offloaded) {
+    set_error("fragment topology is offloaded");
+    return GL_ERR_STATE;
+  }
+  cudaStream_t s = (cudaStream_t) stream;
+  switch (op->kind) {
+    case GL_OP_BFS_LEVEL: {
+      GL_ARG(op->state, "state required");
+      OpLevel o{(uint32_t*) op->state, op->out_bitmap, op->depth};
+      return scan_queue(f, s, queue, n, o, lb, entries_scanned_host);
+    }
+    case GL_OP_MIN_RELAX_U32: {
+      GL_ARG(op->state, "state required");
+      OpMinU32 o{(uint32_t*) op->state, op->out_bitmap, op->use_weight && f->oe.w && f->edata_bytes == 4};
+      return scan_queue(f, s, queue, n, o, lb, entries_scanned_host);
+    }
+    case GL_OP_MIN_RELAX_F32: {
+      GL_ARG(op->state, "state required");
+      OpMinF32 o{(float*) op->state, op->out_bitmap, op->use_weight && f->oe.w && f->edata_bytes == 4};
+      return scan_queue(f, s, queue, n, o, lb, entries_scanned_host);
+    }
+    case GL_OP_ADD_SCATTER_F64: {
+      GL_ARG(op->state && op->state2, "state and state2 required");
+      OpAddF64 o{(const double*) op->state, (double*) op->state2};
+      return scan_queue(f, s, queue, n, o, lb, entries_scanned_host);
+    }
+    case GL_OP_COUNT: {
+      OpCount o{nullptr};
+      return scan_queue(f, s, queue, n, o, lb, entries_scanned_host);
+    }
+    default:
+      set_error("unknown edge op %d", op->kind);
+      return GL_ERR_ARG;
+  }
+}
+
+int gl_compact_bitmap(void* stream, const uint32_t* bitmap, uint32_t n_bits,
+                      uint32_t* queue_out, uint32_t* count_host) {
+  GL_ARG(bitmap && queue_out && count_host, "null argument");
+  cudaStream_t s = (cudaStream_t) stream;
+  DeviceInfo* di;
+  GL_TRY(device_info(&di));
+  uint32_t* d_count = nullptr;
+  GL_CUDA(cudaMalloc(&d_count, 4));
+  GL_CUDA(cudaMemsetAsync(d_count, 0, 4, s));
+  int g = std::max(1, std::min<int>(di->sm_count * 8, (int) ((n_bits + kTB - 1) / kTB)));
+  k_compact<<<g, kTB, 0, s>>>(bitmap, n_bits, queue_out, d_count);
+  GL_COUNT_LAUNCH();
+  cudaError_t e = cudaMemcpyAsync(count_host, d_count, 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_count);
+  if (e != cudaSuccess) {
+    set_error("gl_compact_bitmap: %s", cudaGetErrorString(e));
+    return GL_ERR_CUDA;
+  }
+  return GL_OK;
+}
+
+}  // extern "C"
