@@ -75,7 +75,8 @@ struct gl_app {
 
 namespace gl {
 gl_app* make_bfs();
-gl_app* make_sssp();
+gl_app* make_sssp_f32();
+gl_app* make_sssp_f64();
 gl_app* make_wcc();
 gl_app* make_pagerank();
 gl_app* make_cdlp();

@@ -1,9 +1,6 @@
 // placeholders until each app lands (gl_app_create reports "not available")
 #include "app_base.h"
 namespace gl {
-gl_app* make_sssp() { return nullptr; }
-gl_app* make_wcc() { return nullptr; }
-gl_app* make_pagerank() { return nullptr; }
 gl_app* make_cdlp() { return nullptr; }
 gl_app* make_lcc() { return nullptr; }
 }  // namespace gl

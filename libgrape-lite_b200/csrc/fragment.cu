@@ -365,6 +365,7 @@ int build_from_producer(gl_frag* f, Producer& prod, uint64_t n, int directed,
   p.hi = std::min<uint64_t>(n, p.lo + p.chunk);
   GL_ARG(n < (1ull << 31), "n_vertices must be < 2^31");
   f->ivnum = (uint32_t) (p.hi - p.lo);
+  f->part_chunk = p.chunk;
   f->total_vnum = n;
   f->directed = directed;
   f->edata_bytes = edata_bytes;

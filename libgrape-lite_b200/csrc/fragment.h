@@ -34,6 +34,7 @@ struct gl_frag {
   int64_t* inner_oids = nullptr;    // device or null
   std::vector<int64_t> h_inner_oids;
   int64_t oid_base = 0;
+  uint64_t part_chunk = 0;  // ceil(n/fnum) of the segmented partitioner (0 = unknown)
   // bitmap of inner vertices with out-degree > 0 (pull candidates)
   uint32_t* nonzero_deg = nullptr;
   uint64_t device_bytes = 0;

@@ -83,7 +83,7 @@ int gl_app_create(gl_app_t** out, int kind, gl_frag_t* frag, gl_comm_t* comm,
   gl_app* a = nullptr;
   switch (kind) {
     case GL_APP_BFS: a = make_bfs(); break;
-    case GL_APP_SSSP: a = make_sssp(); break;
+    case GL_APP_SSSP: a = (cfg && cfg->sssp_f64) ? make_sssp_f64() : make_sssp_f32(); break;
     case GL_APP_WCC: a = make_wcc(); break;
     case GL_APP_PAGERANK: a = make_pagerank(); break;
     case GL_APP_CDLP: a = make_cdlp(); break;

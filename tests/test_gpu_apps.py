@@ -83,3 +83,113 @@ def test_bfs_source_not_in_graph_and_isolated():
         assert r[iso[0]] == 0 and np.sum(r != INT64_MAX) == 1
         app.close()
     frag.close()
+
+
+# ------------------------------------------------------------------ SSSP ----
+def _sssp_render(oids, dist):
+    big = np.finfo(np.float64).max
+    return G.render(oids, ["infinity" if d == big else G.fmt_sci(d) for d in dist])
+
+
+@pytest.mark.parametrize("directed,name", [(False, "p2p-31-SSSP"), (True, "p2p-31-SSSP-directed")])
+@pytest.mark.parametrize("f64", [0, 1])
+def test_sssp_golden(p2p, directed, name, f64):
+    oids, und, dr = p2p
+    app = app_available("sssp", dr if directed else und, source_oid=6, sssp_f64=f64)
+    app.query()
+    dist = app.result()
+    assert _sssp_render(oids, dist) == G.golden_lines(name)
+    app.query()
+    assert np.array_equal(app.result(), dist)
+    app.close()
+
+
+@pytest.mark.parametrize("scale,wmode,f64", [(10, 1, 0), (15, 1, 0), (15, 2, 1), (12, 0, 0)])
+def test_sssp_rmat_vs_oracle(scale, wmode, f64):
+    """Integer weights: f32 sums are exact => bit-exact vs the fp64 oracle.
+    Real weights (multiples of 2^-24): fp64 on device => bit-exact as well."""
+    n, src, dst, w = rmat_graph(scale, seed=3, weight_mode=wmode)
+    g = pyoracle.Graph(n, src, dst, None if w is None else w.astype(np.float64))
+    frag = pkg().Fragment.rmat(scale, 16, seed=3, weight_mode=wmode)
+    source = g.max_degree_vertex()
+    app = app_available("sssp", frag, source_oid=int(source), sssp_f64=f64)
+    app.query()
+    want, _ = g.sssp(source)
+    got = app.result()
+    assert np.array_equal(got, want)
+    app.close()
+    frag.close()
+
+
+def test_sssp_real_weights_f32_within_tolerance():
+    n, src, dst, w = rmat_graph(14, seed=8, weight_mode=2)
+    g = pyoracle.Graph(n, src, dst, w.astype(np.float64))
+    frag = pkg().Fragment.rmat(14, 16, seed=8, weight_mode=2)
+    source = g.max_degree_vertex()
+    app = app_available("sssp", frag, source_oid=int(source))
+    app.query()
+    want, _ = g.sssp(source)
+    got = app.result()
+    fin = want < 1e300
+    assert np.array_equal(got >= 1e300, ~fin)
+    assert np.max(np.abs(got[fin] - want[fin]) / np.maximum(want[fin], 1e-30)) < 1e-6  # north-star tolerance
+    app.close()
+    frag.close()
+
+
+# ------------------------------------------------------------------- WCC ----
+def test_wcc_golden(p2p):
+    oids, und, dr = p2p
+    want = np.array([int(v) for _, v in G.golden_pairs("p2p-31-WCC")])
+    for frag in (und, dr):
+        app = app_available("wcc", frag)
+        app.query()
+        lab = app.result()
+        assert G.same_partition(lab, want)          # misc/wcc_check.cc rule
+        # label = min oid of the component (CPU app convention, wcc.h:139-153)
+        assert np.all(lab <= oids)
+        app.close()
+
+
+@pytest.mark.parametrize("scale", [10, 15])
+def test_wcc_rmat_vs_oracle(scale):
+    n, src, dst, _ = rmat_graph(scale, seed=6)
+    g = pyoracle.Graph(n, src, dst, None)
+    frag = pkg().Fragment.rmat(scale, 16, seed=6)
+    app = app_available("wcc", frag)
+    app.query()
+    want, _ = g.wcc()
+    assert np.array_equal(app.result(), want.astype(np.int64))   # bit-exact min labels
+    app.close()
+    frag.close()
+
+
+# -------------------------------------------------------------- PageRank ----
+@pytest.mark.parametrize("pull", [0, 1])
+def test_pagerank_golden(p2p, pull):
+    oids, und, _ = p2p
+    want = np.array([float(v) for _, v in G.golden_pairs("p2p-31-PR")])
+    app = app_available("pagerank", und, pr_delta=0.85, max_round=10, pr_pull=pull)
+    app.query()
+    got = app.result()
+    assert G.eps_check(got, want, 1e-4)              # the reference's own check
+    assert np.max(np.abs(got - want) / want) < 1e-6  # north-star tolerance
+    app.close()
+
+
+@pytest.mark.parametrize("pull", [0, 1])
+def test_pagerank_rmat_vs_oracle(pull):
+    scale = 14
+    n, src, dst, _ = rmat_graph(scale, seed=2)
+    g = pyoracle.Graph(n, src, dst, None)
+    frag = pkg().Fragment.rmat(scale, 16, seed=2)
+    app = app_available("pagerank", frag, pr_delta=0.85, max_round=10, pr_pull=pull)
+    st = app.query()
+    got = app.result()
+    for mode in (0, 1):
+        want = g.pagerank(0.85, 10, mode)
+        assert np.max(np.abs(got - want) / want) < 1e-6
+    assert abs(got.sum() - 1.0) < 1e-9
+    assert st.supersteps == 12        # PEval + 10 updates + the final message round
+    app.close()
+    frag.close()
