@@ -193,3 +193,50 @@ def test_pagerank_rmat_vs_oracle(pull):
     assert st.supersteps == 12        # PEval + 10 updates + the final message round
     app.close()
     frag.close()
+
+
+# ------------------------------------------------------------------ CDLP ----
+def test_cdlp_golden(p2p):
+    oids, und, _ = p2p
+    app = app_available("cdlp", und, max_round=10)
+    app.query()
+    lab = app.result()
+    assert G.render(oids, [str(int(x)) for x in lab]) == G.golden_lines("p2p-31-CDLP")
+    app.close()
+
+
+@pytest.mark.parametrize("scale,rounds", [(10, 10), (14, 5), (8, 0), (8, 1)])
+def test_cdlp_rmat_vs_oracle(scale, rounds):
+    n, src, dst, _ = rmat_graph(scale, seed=11)
+    g = pyoracle.Graph(n, src, dst, None)
+    frag = pkg().Fragment.rmat(scale, 16, seed=11)
+    app = app_available("cdlp", frag, max_round=rounds)
+    app.query()
+    assert np.array_equal(app.result(), g.cdlp(rounds))
+    app.close()
+    frag.close()
+
+
+# ------------------------------------------------------------------- LCC ----
+def test_lcc_golden(p2p):
+    oids, und, _ = p2p
+    app = app_available("lcc", und)
+    app.query()
+    lcc = app.result()
+    assert G.render(oids, [G.fmt_sci(x) for x in lcc]) == G.golden_lines("p2p-31-LCC")
+    app.close()
+
+
+@pytest.mark.parametrize("scale", [8, 12])
+def test_lcc_rmat_vs_oracle(scale):
+    """R-MAT keeps duplicate edges and self loops, so this pins the
+    multiplicity rules of lcc.h:96-190."""
+    n, src, dst, _ = rmat_graph(scale, seed=13)
+    g = pyoracle.Graph(n, src, dst, None)
+    frag = pkg().Fragment.rmat(scale, 16, seed=13)
+    app = app_available("lcc", frag)
+    app.query()
+    want, _ = g.lcc()
+    assert np.array_equal(app.result(), want)    # same integers, same fp64 division
+    app.close()
+    frag.close()
