@@ -1,0 +1,107 @@
+"""Runs oracle/_ref/ref_driver — the UNMODIFIED reference CPU apps compiled
+against functional MPI/glog shims (oracle/ref/).  TEST / MEASUREMENT ONLY."""
+import importlib
+import json
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+EXE = os.path.join(_HERE, "_ref", "ref_driver")
+
+
+def available():
+    return os.path.exists(EXE)
+
+
+def write_graph(path, n, src, dst, w=None, oids=None):
+    src = np.ascontiguousarray(src, dtype=np.int64)
+    dst = np.ascontiguousarray(dst, dtype=np.int64)
+    with open(path, "wb") as f:
+        f.write(b"GRB1")
+        f.write(struct.pack("<qqii", n, len(src), 0 if w is None else 1, 0 if oids is None else 1))
+        if oids is not None:
+            f.write(np.ascontiguousarray(oids, dtype=np.int64).tobytes())
+        f.write(src.tobytes())
+        f.write(dst.tobytes())
+        if w is not None:
+            f.write(np.ascontiguousarray(w, dtype=np.float64).tobytes())
+
+
+def run_app(app, graph_path, directed=False, source=0, pr_d=0.85, mr=10, threads=0, repeat=1,
+            want_output=True, timeout=3600):
+    """-> (info dict, text output or None)"""
+    out = None
+    cmd = [EXE, "--app", app, "--graph", graph_path, "--directed", "1" if directed else "0",
+           "--source", str(int(source)), "--pr_d", repr(float(pr_d)), "--mr", str(int(mr)),
+           "--threads", str(int(threads)), "--repeat", str(int(repeat))]
+    with tempfile.TemporaryDirectory() as d:
+        if want_output:
+            out = os.path.join(d, "out.txt")
+            cmd += ["--out", out]
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+        if p.returncode != 0:
+            raise RuntimeError("ref_driver failed (%d): %s" % (p.returncode, p.stderr[-2000:]))
+        info = json.loads(p.stdout.strip().splitlines()[-1])
+        text = open(out).read() if want_output else None
+    return info, text
+
+
+def parse_output(text, dtype=float):
+    """`oid value` lines -> (oids sorted, values in oid order) — the reference's
+    verifiers sort by the first column (misc/app_tests.sh:7)."""
+    o, v = [], []
+    for line in text.splitlines():
+        a, b = line.split()
+        o.append(int(a))
+        if dtype is float:
+            v.append(np.finfo(np.float64).max if b == "infinity" else float(b))
+        else:
+            v.append(int(b))
+    o = np.array(o, dtype=np.int64)
+    v = np.array(v, dtype=np.float64 if dtype is float else np.int64)
+    k = np.argsort(o, kind="stable")
+    return o[k], v[k]
+
+
+_graph_cache = {}
+
+
+def _rmat_file(scale, edgefactor, seed, weighted):
+    key = (scale, edgefactor, seed, weighted)
+    if key not in _graph_cache:
+        pkg = importlib.import_module("libgrape-lite_b200")
+        src, dst, w = pkg.rmat_edges_host(scale, edgefactor, seed, 1 if weighted else 0)
+        path = os.path.join(tempfile.gettempdir(), "grb_rmat_%d_%d_%d_%d.bin" % key)
+        write_graph(path, 1 << scale, src, dst, None if w is None else w.astype(np.float64))
+        deg = np.bincount(np.concatenate([src, dst]), minlength=1 << scale)
+        source = int(np.argmax(deg))      # max degree, ties -> smallest oid
+        _graph_cache.clear()
+        _graph_cache[key] = (path, source, len(src))
+    return _graph_cache[key]
+
+
+def run(exe, app, scale, edgefactor=16, seed=1):
+    """bench.py CPU arm: one query of the reference CPU app with all host threads."""
+    path, source, m = _rmat_file(scale, edgefactor, seed, app == "sssp")
+    info, text = run_app(app, path, source=source, repeat=1, want_output=(app in ("bfs", "sssp")))
+    ms = float(info["query_ms"][-1])
+    if app in ("bfs", "sssp"):
+        # Graph500 numerator: input edges with a reached endpoint
+        _, vals = parse_output(text, float if app == "sssp" else int)
+        reached = vals < 1e300 if app == "sssp" else vals != np.iinfo(np.int64).max
+        pkg = importlib.import_module("libgrape-lite_b200")
+        src, dst, _ = pkg.rmat_edges_host(scale, edgefactor, seed, 0)
+        edges = int(np.count_nonzero(reached[src]))
+    elif app in ("pagerank", "cdlp"):
+        edges = m * 10
+    else:
+        edges = m
+    return {"value": edges / (ms * 1e-3), "unit": "edges/s", "ms": ms, "cores": int(info["threads"]),
+            "kind": "reference",
+            "sample": "%s on R-MAT scale-%d (same generator/seed as the GPU arm), one Query() of the "
+                      "unmodified reference CPU app (ParallelEngine, %d threads of %d)"
+                      % (app.upper(), scale, info["threads"], info["hardware_concurrency"])}
