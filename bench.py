@@ -156,6 +156,7 @@ def run_gpu(args):
     cfg = dict(source_oid=int(src_oid), lb=args.lb)
     if args.app == "bfs":
         cfg["direction_opt"] = 0 if args.push_only else 1
+        cfg["fuse_supersteps"] = 0 if args.no_fuse else 1
     if args.app in ("pagerank", "cdlp"):
         cfg["max_round"] = 10
     app = pkg.App(args.app, frag, comm, **cfg)
@@ -343,6 +344,7 @@ def main():
     ap.add_argument("--push-only", action="store_true")
     ap.add_argument("--cpu-scale", type=int, default=22, help="largest scale the CPU arm runs (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="one launch per superstep (profiling) instead of the fused query kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -6,12 +6,32 @@
 // unreachable = INT64_MAX (bfs.h:31,40-45).  Levels are order-independent, so
 // any push/pull schedule yields bit-identical output.
 //
-// B200 re-design: levels kept as u32 + a visited bitmap that stays L2
-// resident (2 MB at scale 24); the frontier is a bitmap consumed by the fused
-// tile kernel (no O(V) compaction pass, no per-round Count() syncs: one
-// control-block read per superstep); the pull step builds its result words in
-// shared memory and writes each bitmap word once.
+// B200 re-design
+//  * No per-vertex depth array on the hot path.  Level d IS a bitmap
+//    (lv[d], 2 MB at scale 24) plus one visited bitmap; both stay L2 resident.
+//    The int64 depth array the reference exposes is materialised once, with
+//    coalesced reads/writes, when the result is requested.  This removes the
+//    reference's scattered 8-byte depth writes (bfs.h:195-196) and the 8 B x V
+//    state initialisation from every query.
+//  * Push levels run the engine's fused frontier scan (engine.cuh).
+//  * Pull levels test, for every unvisited vertex, its highest-degree
+//    neighbour first (hub_nbr[], built once in Setup like the reference's
+//    PrepareToRunApp artefacts): one coalesced 4-byte load + one L2-resident
+//    bitmap probe resolves most candidates without touching row pointers or
+//    column indices; the rest fall back to the row scan of bfs.h:239-259.
+//  * Single fragment: the whole query is ONE cooperative launch
+//    (k_bfs_fused); grid.sync() replaces the reference's 4 host
+//    synchronisations per round (bfs.h:169-170,189,263).  Multi-fragment runs
+//    keep one launch group per superstep around the halo exchange.
+#include <cooperative_groups.h>
+
 #include "apps_common.cuh"
+
+namespace cg = cooperative_groups;
+
+#ifndef GL_BFS_FUSED_CTAS
+#define GL_BFS_FUSED_CTAS 8
+#endif
 
 namespace gl {
 namespace {
@@ -20,21 +40,18 @@ struct OpBfsPush {
   using Meta = uint32_t;
   using W = float;
   static constexpr bool kWeighted = false;
-  uint32_t* level;
   uint32_t* vis;
   uint32_t* nxt;
   uint32_t* remote;
   const uint64_t* rp;
   uint32_t ivnum;
-  uint32_t next_depth;
   GL_DEV Meta assign(uint32_t) const { return 0; }
   GL_DEV void edge(uint32_t, Meta, uint32_t v, W, ScanAcc& acc) const {
     if (bit_test(vis, v)) return;        // plain (possibly stale) read first
     if (!bit_set_atomic(vis, v)) return; // somebody else won
-    level[v] = next_depth;
+    bit_set_atomic(nxt, v);              // level bitmap of depth+1 (also for outer v)
     acc.touched++;
     if (v < ivnum) {
-      bit_set_atomic(nxt, v);
       acc.next_count++;
       acc.next_edges += rp[v + 1] - rp[v];
     } else {
@@ -44,98 +61,166 @@ struct OpBfsPush {
   }
 };
 
-__global__ void k_bfs_seed(uint32_t src, uint32_t* level, uint32_t* cur,
-                           uint32_t* vis) {
+__global__ void k_bfs_seed(uint32_t src, uint32_t* lv0, uint32_t* vis) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    level[src] = 0;
-    cur[src >> 5] |= 1u << (src & 31);
+    lv0[src >> 5] |= 1u << (src & 31);
     vis[src >> 5] |= 1u << (src & 31);
   }
 }
 
-// Pull step over the inner vertices (bfs.h:239-259): every unvisited,
-// non-isolated inner vertex looks for a parent in the current frontier among
-// its inner neighbours [rp[v], row_end[v]).
-__global__ void __launch_bounds__(kTB)
-k_bfs_pull(const uint64_t* __restrict__ rp, const uint64_t* __restrict__ row_end,
-           const uint32_t* __restrict__ col, uint32_t ivnum,
-           const uint32_t* __restrict__ cur, uint32_t* vis, uint32_t* nxt,
-           const uint32_t* __restrict__ nz, uint32_t* level,
-           uint32_t next_depth, ScanCtrl* ctrl) {
-  __shared__ uint32_t s_v[kTileV];
-  __shared__ uint32_t s_found[kTileV / 32];
-  __shared__ uint32_t s_warp[kTB / 32 + 1];
-  __shared__ uint32_t s_tile;
-  const uint32_t ntiles = (ivnum + kTileV - 1) / kTileV;
-  const uint32_t nwords = (ivnum + 31) / 32;
-  ScanAcc acc;
-  uint64_t scanned = 0;
-  for (;;) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(&ctrl->tile_ticket, 1u);
-    if (threadIdx.x < kTileV / 32) s_found[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= ntiles) break;
-    const uint32_t widx = tile * (kTileV / 32) + (threadIdx.x >> 3);
-    uint32_t word = widx < nwords ? (nz[widx] & ~vis[widx]) : 0u;
-    uint32_t nib = (word >> ((threadIdx.x & 7) * 4)) & 0xFu;
-    uint32_t nc;
-    uint32_t off = block_excl_scan(__popc(nib), s_warp, &nc);
-    if (nc == 0) continue;
-    const uint32_t vbase = tile * kTileV + threadIdx.x * 4;
-    while (nib) {
-      uint32_t b = __ffs(nib) - 1;
-      nib &= nib - 1;
-      s_v[off++] = vbase + b;
+// hub_nbr[v] = the inner neighbour of v with the largest out-degree (ties ->
+// first in the row); one warp per row.  Built once per app.
+__global__ void __launch_bounds__(256)
+k_bfs_hub_nbr(const uint64_t* __restrict__ rp, const uint64_t* __restrict__ row_end,
+              const uint32_t* __restrict__ col, uint32_t ivnum, uint32_t* hub_nbr) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < ivnum; v += warps) {
+    const uint64_t b = rp[v], e = row_end[v];
+    unsigned long long best = 0;
+    for (uint64_t p = b + lane_id(); p < e; p += 32) {
+      uint32_t u = col[p];
+      unsigned long long dg = rp[u + 1] - rp[u];
+      if (dg > 0xFFFFFFFFull) dg = 0xFFFFFFFFull;
+      uint64_t off = p - b;
+      if (off > 0xFFFFFFFEull) off = 0xFFFFFFFEull;
+      unsigned long long key = (dg << 32) | (0xFFFFFFFFu - (uint32_t) off);
+      best = key > best ? key : best;
     }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nc; i += kTB) {
-      const uint32_t v = s_v[i];
-      const uint64_t b = rp[v];
-      const uint64_t e = row_end[v];
-      bool found = false;
-      uint64_t p = b;
-      for (; p < e; ++p) {
-        uint32_t u = col[p];
-        if (bit_test(cur, u)) {
-          found = true;
-          ++p;
-          break;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+      best = t > best ? t : best;
+    }
+    if (lane_id() == 0) hub_nbr[v] = (b < e) ? col[b + (0xFFFFFFFFu - (uint32_t) best)] : kInfU32;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Pull step over the inner vertices (bfs.h:239-259) as a phase shared by the
+// stand-alone kernel and the fused whole-query kernel.
+// ---------------------------------------------------------------------------
+struct PullSmem {
+  uint32_t v[kTileV];
+  uint32_t found[kTileV / 32];
+  uint32_t words[kTB];
+  uint32_t warp[kTB / 32 + 1];
+  uint32_t nz[kSuperTiles];
+  uint32_t ticket;
+};
+
+struct PullArgs {
+  const uint64_t* rp;
+  const uint64_t* row_end;   // end of the inner-neighbour part of each row
+  const uint32_t* col;
+  const uint32_t* hub_nbr;
+  uint32_t ivnum;
+  const uint32_t* nz;
+};
+
+// One super-tile = 8192 vertices = 256 words; thread t owns word t: it probes
+// the hub neighbour of each of its (up to 32) candidates with eight
+// independent 16-byte loads in flight (stage 1), hands the unresolved ones to
+// a CTA-wide row scan (stage 2) and finally writes its visited / next-level
+// word with plain stores (the word belongs to this thread during the pull).
+GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
+                           const uint32_t* __restrict__ cur, uint32_t* vis,
+                           uint32_t* nxt, ScanCtrl* ctrl, ScanAcc& acc) {
+  const uint32_t nwords = (a.ivnum + 31) / 32;
+  uint64_t scanned = 0;
+  uint32_t cand = 0;
+  uint32_t st;
+  while (next_super_tile(sm, &ctrl->tile_ticket, a.ivnum,
+                         [&](uint32_t w) { return a.nz[w] & ~vis[w]; }, &st)) {
+    const uint32_t word = sm.words[threadIdx.x];
+    const uint32_t wi = st * (kSuperV / 32) + threadIdx.x;
+    const uint32_t vbase = wi * 32;
+    sm.words[threadIdx.x] = 0;  // reused as the stage-2 result word
+    // ---- stage 1 ----
+    uint32_t res = 0;
+    if (word) {
+      const uint4* hp = (const uint4*) (a.hub_nbr + vbase);
+#pragma unroll 4
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t nib = (word >> (4 * j)) & 0xFu;
+        if (nib) {
+          const uint4 h = hp[j];
+          // kInfU32 = the row has no inner neighbour
+          uint32_t r = 0;
+          if ((nib & 1u) && h.x != kInfU32 && bit_test(cur, h.x)) r |= 1u;
+          if ((nib & 2u) && h.y != kInfU32 && bit_test(cur, h.y)) r |= 2u;
+          if ((nib & 4u) && h.z != kInfU32 && bit_test(cur, h.z)) r |= 4u;
+          if ((nib & 8u) && h.w != kInfU32 && bit_test(cur, h.w)) r |= 8u;
+          res |= r << (4 * j);
         }
       }
-      scanned += p - b;
-      if (found) {
-        level[v] = next_depth;
-        atomicOr(&s_found[(v & (kTileV - 1)) >> 5], 1u << (v & 31));
-        acc.next_count++;
-        acc.touched++;
-        acc.next_edges += rp[v + 1] - b;
-      }
+      scanned += __popc(word);
     }
-    __syncthreads();
-    if (threadIdx.x < kTileV / 32) {
-      uint32_t w = s_found[threadIdx.x];
-      uint32_t wi = tile * (kTileV / 32) + threadIdx.x;
-      if (w && wi < nwords) {
-        vis[wi] |= w;  // the word is owned by this tile during the pull
-        nxt[wi] = w;
+    // ---- stage 2: leftovers scan their row, kTileV candidates per pass ----
+    uint32_t rest = word & ~res;
+    uint32_t total;
+    uint32_t off = block_excl_scan(__popc(rest), sm.warp, &total);
+    cand += (threadIdx.x == 0) ? total : 0;
+    for (uint32_t base = 0; base < total; base += kTileV) {
+      // stage the candidates whose rank falls in [base, base + kTileV)
+      uint32_t r = rest, k = off;
+      while (r) {
+        uint32_t b = __ffs(r) - 1;
+        r &= r - 1;
+        if (k >= base && k < base + kTileV) sm.v[k - base] = vbase + b;
+        ++k;
       }
+      __syncthreads();
+      const uint32_t nc = (total - base) < (uint32_t) kTileV ? (total - base) : (uint32_t) kTileV;
+      for (uint32_t i = threadIdx.x; i < nc; i += kTB) {
+        const uint32_t v = sm.v[i];
+        const uint64_t b = a.rp[v];
+        const uint32_t len = (uint32_t) (a.row_end[v] - b);
+        const uint32_t* row = a.col + b;
+        bool found = false;
+        uint32_t p = 0;
+        for (; p < len; ++p) {
+          if (bit_test(cur, row[p])) {
+            found = true;
+            ++p;
+            break;
+          }
+        }
+        scanned += p;
+        if (found) atomicOr(&sm.words[(v >> 5) - st * (kSuperV / 32)], 1u << (v & 31));
+      }
+      __syncthreads();
     }
+    if (total == 0) __syncthreads();  // sm.words zeroing vs. the next ticket
+    const uint32_t found_w = res | sm.words[threadIdx.x];
+    if (found_w && wi < nwords) {
+      vis[wi] |= found_w;  // the word is owned by this thread during the pull
+      nxt[wi] = found_w;
+    }
+    acc.next_count += __popc(found_w);
     __syncthreads();
   }
-  flush_acc(acc, ctrl);
+  acc.touched = acc.next_count;
   unsigned long long s = warp_sum((unsigned long long) scanned);
   if (lane_id() == 0 && s) atomicAdd(&ctrl->scanned, s);
+  if (threadIdx.x == 0 && cand) atomicAdd(&ctrl->frontier, (unsigned long long) cand);
+}
+
+__global__ void __launch_bounds__(kTB, 8)
+k_bfs_pull(PullArgs a, const uint32_t* __restrict__ cur, uint32_t* vis,
+           uint32_t* nxt, ScanCtrl* ctrl) {
+  __shared__ PullSmem sm;
+  ScanAcc acc;
+  bfs_pull_phase(sm, a, cur, vis, nxt, ctrl, acc);
+  flush_acc(acc, ctrl);
 }
 
 // Pull step over the outer vertices (bfs.h:210-223): an unvisited outer vertex
-// whose reverse adjacency holds a frontier vertex takes next_depth and is
+// whose reverse adjacency holds a frontier vertex joins level depth+1 and is
 // reported to its owner.
 __global__ void __launch_bounds__(kTB)
 k_bfs_pull_outer(const uint64_t* __restrict__ orp, const uint32_t* __restrict__ ocol,
                  uint32_t ivnum, uint32_t ovnum, const uint32_t* __restrict__ cur,
-                 uint32_t* vis, uint32_t* remote, uint32_t* level,
-                 uint32_t next_depth, ScanCtrl* ctrl) {
+                 uint32_t* vis, uint32_t* nxt, uint32_t* remote, ScanCtrl* ctrl) {
   ScanAcc acc;
   uint64_t scanned = 0;
   for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < ovnum;
@@ -153,8 +238,8 @@ k_bfs_pull_outer(const uint64_t* __restrict__ orp, const uint32_t* __restrict__ 
     }
     scanned += p - b;
     if (found) {
-      level[v] = next_depth;
       bit_set_atomic(vis, v);
+      bit_set_atomic(nxt, v);
       bit_set_atomic(remote, v);
       acc.remote++;
       acc.touched++;
@@ -165,19 +250,157 @@ k_bfs_pull_outer(const uint64_t* __restrict__ orp, const uint32_t* __restrict__ 
   if (lane_id() == 0 && s) atomicAdd(&ctrl->scanned, s);
 }
 
+// ---------------------------------------------------------------------------
+// Fused whole-query BFS (single fragment): ONE cooperative launch runs every
+// superstep.  Per-level device timestamps keep the ms/superstep report.
+// ---------------------------------------------------------------------------
+constexpr int kMaxFusedStats = 480;
+struct BfsLevelStat {
+  unsigned long long t_ns;
+  unsigned long long scanned;
+  uint32_t frontier;
+  uint32_t mode;
+};
+struct BfsFusedCtl {
+  ScanCtrl c[3];       // rotating per-level counters (level d uses c[d % 3])
+  uint32_t levels;     // levels executed
+  uint32_t has_src;
+  uint32_t overflow;   // ran out of level bitmaps
+  uint32_t pad;
+  unsigned long long src_deg, m_total, touched;
+  unsigned long long t_begin;
+  BfsLevelStat stat[kMaxFusedStats];
+};
+
+GL_DEV unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// push -> pull when the frontier's edges exceed 1/14 of the unvisited edges;
+// pull -> push (for good) when the frontier shrinks below V/24 (Beamer et
+// al.; the reference uses vertex ratios, bfs.h:171-180 — the schedule only
+// affects speed, never the levels).  phase: 0 = initial push, 1 = pull,
+// 2 = final push.
+GL_DEV uint32_t bfs_next_phase(uint32_t phase, unsigned long long n_f,
+                               unsigned long long m_f, unsigned long long m_u,
+                               uint32_t ivnum, int direction_opt) {
+  if (!direction_opt) return 0;
+  if (phase == 0) return m_f > m_u / 14 ? 1u : 0u;
+  if (phase == 1) return n_f >= (unsigned long long) ivnum / 24 ? 1u : 2u;
+  return 2u;
+}
+
+__global__ void k_bfs_seed_fused(uint32_t src, int has_src, uint32_t* lv0,
+                                 uint32_t* vis, const uint64_t* rp,
+                                 unsigned long long m_total, BfsFusedCtl* ctl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->c[0] = ScanCtrl();
+  ctl->c[1] = ScanCtrl();
+  ctl->c[2] = ScanCtrl();
+  ctl->levels = 0;
+  ctl->overflow = 0;
+  ctl->touched = 0;
+  ctl->m_total = m_total;
+  unsigned long long deg = 0;
+  if (has_src) {
+    lv0[src >> 5] |= 1u << (src & 31);
+    vis[src >> 5] |= 1u << (src & 31);
+    deg = rp[src + 1] - rp[src];
+  }
+  ctl->has_src = has_src;
+  ctl->src_deg = deg;
+  ctl->t_begin = global_ns();
+}
+
+struct BfsFusedArgs {
+  PullArgs pa;
+  EdgeRange er;
+  uint32_t* lv;      // level bitmaps: lv + d*words
+  uint32_t words;
+  uint32_t max_lv;   // number of level bitmaps available
+  uint32_t* vis;
+  int direction_opt;
+  BfsFusedCtl* ctl;
+  HubItem* hubs;
+  uint32_t hub_cap, hub_deg;
+};
+
+// Level d reads lv[d] and writes lv[d+1] (pre-zeroed).  Every thread derives
+// the push/pull decision from the same counters, so nothing is published
+// between levels: one grid.sync per pull level, two per push level (tile
+// phase | hub phase).
+__global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ union {
+    ScanSmem<uint32_t> scan;
+    PullSmem pull;
+  } sm;
+  __shared__ uint32_t s_item;
+  BfsFusedCtl* ctl = a.ctl;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  // running totals, replicated in every thread
+  unsigned long long n_f = ctl->has_src ? 1 : 0;
+  unsigned long long m_f = ctl->src_deg;
+  unsigned long long visited_edges = m_f;
+  const unsigned long long m_total = ctl->m_total;
+  uint32_t phase = bfs_next_phase(0, n_f, m_f, m_total - visited_edges, a.pa.ivnum, a.direction_opt);
+  for (uint32_t depth = 0; n_f != 0; ++depth) {
+    if (depth + 1 >= a.max_lv) {
+      if (gtid == 0) ctl->overflow = 1;
+      break;
+    }
+    ScanCtrl* C = &ctl->c[depth % 3];
+    const uint32_t* cur = a.lv + (size_t) depth * a.words;
+    uint32_t* nxt = a.lv + (size_t) (depth + 1) * a.words;
+    ScanAcc acc;
+    if (phase != 1) {
+      OpBfsPush op{a.vis, nxt, nullptr, a.er.rp, a.pa.ivnum};
+      frontier_scan_phase<OpBfsPush>(sm.scan, cur, a.pa.ivnum, a.er, op, C, a.hubs, a.hub_cap, a.hub_deg, acc);
+      grid.sync();
+      hub_scan_phase<OpBfsPush>(&s_item, a.er, op, C, a.hubs, a.hub_cap, acc);
+    } else {
+      bfs_pull_phase(sm.pull, a.pa, cur, a.vis, nxt, C, acc);
+    }
+    flush_acc(acc, C);
+    grid.sync();
+    const volatile ScanCtrl* VC = C;
+    const unsigned long long next_count = VC->next_count;
+    const unsigned long long next_edges = VC->next_edges;
+    if (gtid == 0) {
+      if (depth < (uint32_t) kMaxFusedStats) {
+        BfsLevelStat ls;
+        ls.t_ns = global_ns();
+        ls.scanned = VC->scanned;
+        ls.frontier = (uint32_t) (n_f > 0xFFFFFFFFull ? 0xFFFFFFFFull : n_f);
+        ls.mode = phase == 1 ? 1u : 0u;
+        ctl->stat[depth] = ls;
+      }
+      ctl->levels = depth + 1;
+      ctl->touched += VC->touched;
+      // c[(depth+2)%3] was last read right after the previous level's barrier
+      ctl->c[(depth + 2) % 3] = ScanCtrl();
+    }
+    n_f = next_count;
+    m_f = next_edges;
+    visited_edges += next_edges;
+    phase = bfs_next_phase(phase, n_f, m_f,
+                           m_total > visited_edges ? m_total - visited_edges : 0,
+                           a.pa.ivnum, a.direction_opt);
+  }
+}
+
 struct BfsPayload {
   GL_DEV ItemU32 operator()(uint32_t, uint32_t lid) const { return ItemU32{lid}; }
 };
 struct BfsApply {
-  uint32_t* level;
   uint32_t* cur;
   uint32_t* vis;
   const uint64_t* rp;
-  uint32_t depth;
   GL_DEV void operator()(const ItemU32& it, ScanAcc& acc) const {
     uint32_t v = it.lid;
     if (bit_set_atomic(vis, v)) {  // bfs.h:158-166 (curr_depth < depth[v])
-      level[v] = depth;
       bit_set_atomic(cur, v);
       acc.aux++;
       acc.next_edges += rp[v + 1] - rp[v];
@@ -185,118 +408,216 @@ struct BfsApply {
   }
 };
 
-__global__ void k_level_to_depth(const uint32_t* level, uint32_t n, int64_t* out) {
+// depth[v] = first level whose bitmap holds v (coalesced: a warp shares words)
+__global__ void k_depth_from_levels(const uint32_t* lv, uint32_t words,
+                                    uint32_t nlevels, uint32_t n, int64_t* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    uint32_t l = level[i];
-    out[i] = l == kInfU32 ? INT64_MAX : (int64_t) l;
+  if (i >= n) return;
+  int64_t d = INT64_MAX;
+  const uint32_t w = i >> 5, m = 1u << (i & 31);
+  for (uint32_t l = 0; l < nlevels; ++l) {
+    if (lv[(size_t) l * words + w] & m) {
+      d = (int64_t) l;
+      break;
+    }
   }
+  out[i] = d;
 }
 
 struct BfsApp : gl_app {
-  uint32_t *level = nullptr, *cur = nullptr, *nxt = nullptr, *vis = nullptr,
-           *remote = nullptr;
+  uint32_t *lv = nullptr, *vis = nullptr, *remote = nullptr, *hub_nbr = nullptr;
   int64_t* out64 = nullptr;
   size_t words = 0;
   uint32_t tvnum = 0;
+  uint32_t max_lv = 0;
+  uint32_t used_lv = 0;     // level bitmaps dirtied by the previous query
   uint32_t curr_depth = 0;
-  // frontier statistics driving the push/pull switch
-  uint64_t n_f = 0, m_f = 0, visited_edges = 0, visited_cnt = 0;
-  bool pulling = false;
+  // frontier statistics driving the push/pull switch (stepwise path)
+  uint64_t n_f = 0, m_f = 0, visited_edges = 0;
+  uint32_t phase = 0;
+  BfsFusedCtl* d_ctl = nullptr;
+  BfsFusedCtl* h_ctl = nullptr;
+  int fused_grid = 0;
 
   ~BfsApp() override {
-    cudaFree(level);
-    cudaFree(cur);
-    cudaFree(nxt);
+    cudaFree(d_ctl);
+    if (h_ctl) cudaFreeHost(h_ctl);
+    cudaFree(lv);
     cudaFree(vis);
     cudaFree(remote);
+    cudaFree(hub_nbr);
     cudaFree(out64);
   }
   size_t ResultElemBytes() const override { return sizeof(int64_t); }
 
+  uint32_t* level_bm(uint32_t d) { return lv + (size_t) d * words; }
+  const uint64_t* row_end() const { return fv.fnum > 1 ? fv.oe_split : fv.oe_rp + 1; }
+
+  // directed graphs: the pull step would need the incoming adjacency
+  // (bfs.h:225-238); levels are identical with push only.
+  bool can_pull() const { return cfg.direction_opt && !(fv.directed && !frag->ie_alias_oe); }
+
   int Setup() override {
     tvnum = fv.ivnum + fv.ovnum;
-    words = bm_words(tvnum) + 1;
-    GL_CUDA(cudaMalloc(&level, sizeof(uint32_t) * std::max<uint32_t>(tvnum, 1)));
-    GL_CUDA(cudaMalloc(&cur, sizeof(uint32_t) * words));
-    GL_CUDA(cudaMalloc(&nxt, sizeof(uint32_t) * words));
+    words = (bm_words(tvnum) + 4) & ~(size_t) 3;
+    // one bitmap per BFS level: up to 1 GiB of them, at most 4096
+    size_t budget = (size_t) 1 << 30;
+    max_lv = (uint32_t) std::max<size_t>(16, std::min<size_t>(4096, budget / (words * 4)));
+    GL_CUDA(cudaMalloc(&lv, sizeof(uint32_t) * words * max_lv));
+    GL_CUDA(cudaMemsetAsync(lv, 0, sizeof(uint32_t) * words * max_lv, eng.stream));
     GL_CUDA(cudaMalloc(&vis, sizeof(uint32_t) * words));
     GL_CUDA(cudaMalloc(&remote, sizeof(uint32_t) * words));
+    GL_CUDA(cudaMalloc(&hub_nbr, sizeof(uint32_t) * ((size_t) fv.ivnum + kSuperV)));
+    GL_CUDA(cudaMemsetAsync(hub_nbr, 0xFF, sizeof(uint32_t) * ((size_t) fv.ivnum + kSuperV), eng.stream));
     GL_CUDA(cudaMalloc(&out64, sizeof(int64_t) * std::max<uint32_t>(fv.ivnum, 1)));
+    GL_CUDA(cudaMalloc(&d_ctl, sizeof(BfsFusedCtl)));
+    GL_CUDA(cudaMallocHost(&h_ctl, sizeof(BfsFusedCtl)));
+    memset(h_ctl, 0, sizeof(BfsFusedCtl));
+    if (fv.ivnum && can_pull())
+      GL_LAUNCH(k_bfs_hub_nbr, eng.sm_count * 8, 256, eng.stream, fv.oe_rp, row_end(), fv.oe_col, fv.ivnum, hub_nbr);
+    GL_CUDA(cudaStreamSynchronize(eng.stream));
+    used_lv = 0;
     // message = bare lid (bfs.h:50-51: sizeof(vid_t) per outer vertex)
     return mm.Init(comm, fv, sizeof(ItemU32));
   }
 
   int Init() override {
     cudaStream_t s = eng.stream;
-    GL_CUDA(cudaMemsetAsync(level, 0xFF, sizeof(uint32_t) * tvnum, s));
-    GL_CUDA(cudaMemsetAsync(cur, 0, sizeof(uint32_t) * words, s));
-    GL_CUDA(cudaMemsetAsync(nxt, 0, sizeof(uint32_t) * words, s));
+    uint32_t dirty = std::min<uint32_t>(max_lv, used_lv + 2);
+    GL_CUDA(cudaMemsetAsync(lv, 0, sizeof(uint32_t) * words * dirty, s));
     GL_CUDA(cudaMemsetAsync(vis, 0, sizeof(uint32_t) * words, s));
     GL_CUDA(cudaMemsetAsync(remote, 0, sizeof(uint32_t) * words, s));
     curr_depth = 0;
-    n_f = m_f = visited_edges = visited_cnt = 0;
-    pulling = false;
+    used_lv = 0;
+    n_f = m_f = visited_edges = 0;
+    phase = 0;
     return GL_OK;
   }
 
+  PullArgs pull_args() const {
+    return PullArgs{fv.oe_rp, row_end(), fv.oe_col, hub_nbr, fv.ivnum, frag->nonzero_deg};
+  }
+
+  bool fused() const { return cfg.fuse_supersteps && fv.fnum == 1; }
+
+  // Fused path: the whole query is one cooperative launch (PEval seeds and
+  // launches; no IncEval round is needed afterwards).
+  int RunFused() {
+    cudaStream_t s = eng.stream;
+    uint32_t src = 0;
+    int has_src = gl_frag_oid2lid(frag, cfg.source_oid, &src) == GL_OK;
+    GL_LAUNCH(k_bfs_seed_fused, 1, 32, s, src, has_src, level_bm(0), vis, fv.oe_rp,
+              (unsigned long long) frag->oe.entries, d_ctl);
+    BfsFusedArgs a;
+    a.pa = pull_args();
+    a.er = EdgeRange{fv.oe_rp, fv.oe_col, nullptr};
+    a.lv = lv;
+    a.words = (uint32_t) words;
+    a.max_lv = max_lv;
+    a.vis = vis;
+    a.direction_opt = can_pull() ? 1 : 0;
+    a.ctl = d_ctl;
+    a.hubs = eng.hubs;
+    a.hub_cap = eng.hub_cap;
+    a.hub_deg = eng.hub_deg;
+    if (!fused_grid) fused_grid = persistent_grid(k_bfs_fused, eng.sm_count);
+    void* args[] = {&a};
+    GL_CUDA(cudaLaunchCooperativeKernel((void*) k_bfs_fused, dim3(fused_grid), dim3(kTB), args, 0, s));
+    GL_COUNT_LAUNCH();
+    GL_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BfsFusedCtl), cudaMemcpyDeviceToHost, s));
+    GL_CUDA(cudaStreamSynchronize(s));
+    used_lv = h_ctl->levels + 1;
+    if (h_ctl->overflow) {
+      set_error("BFS deeper than %u levels: level-bitmap storage exhausted", max_lv);
+      return GL_ERR_STATE;
+    }
+    q_touched += h_ctl->touched;
+    for (uint32_t i = 0; i < h_ctl->levels && i < (uint32_t) kMaxFusedStats; ++i)
+      note_step(h_ctl->stat[i].scanned, h_ctl->stat[i].frontier, (int) h_ctl->stat[i].mode);
+    return GL_OK;
+  }
+
+  // per-level device timestamps -> ms/superstep of the fused run
+  void FillStats(gl_query_stats* st) override {
+    if (!fused() || !h_ctl) return;
+    uint32_t L = std::min<uint32_t>(h_ctl->levels, (uint32_t) kMaxFusedStats);
+    st->supersteps = (int) L + 1;
+    int n = (int) std::min<uint32_t>(L + 1, GL_MAX_STEP_STATS);
+    st->n_steps = n;
+    unsigned long long prev = h_ctl->t_begin;
+    st->step_ms[0] = 0.f;  // PEval (seed) is part of the launch prologue
+    for (int i = 1; i < n; ++i) {
+      const BfsLevelStat& ls = h_ctl->stat[i - 1];
+      st->step_ms[i] = (float) ((double) (ls.t_ns - prev) * 1e-6);
+      st->step_entries[i] = ls.scanned;
+      st->step_frontier[i] = ls.frontier;
+      st->step_mode[i] = (uint8_t) ls.mode;
+      prev = ls.t_ns;
+    }
+  }
+
   int PEval() override {
+    if (fused()) return RunFused();
     uint32_t src;
     if (gl_frag_oid2lid(frag, cfg.source_oid, &src) == GL_OK) {
-      GL_LAUNCH(k_bfs_seed, 1, 32, eng.stream, src, level, cur, vis);
+      GL_LAUNCH(k_bfs_seed, 1, 32, eng.stream, src, level_bm(0), vis);
       uint64_t rp2[2];
       GL_CUDA(cudaMemcpyAsync(rp2, fv.oe_rp + src, sizeof(rp2), cudaMemcpyDeviceToHost, eng.stream));
       GL_CUDA(cudaStreamSynchronize(eng.stream));
       n_f = 1;
       m_f = rp2[1] - rp2[0];
-      visited_cnt = 1;
       visited_edges = m_f;
     }
+    used_lv = 1;
     mm.ForceContinue();
     return GL_OK;
   }
 
   int IncEval() override {
     cudaStream_t s = eng.stream;
-    const uint32_t next_depth = curr_depth + 1;
+    if (curr_depth + 1 >= max_lv) {
+      set_error("BFS deeper than %u levels: level-bitmap storage exhausted", max_lv);
+      return GL_ERR_STATE;
+    }
+    uint32_t* cur = level_bm(curr_depth);
+    uint32_t* nxt = level_bm(curr_depth + 1);
     GL_TRY(eng.reset_ctrl());
     if (fv.fnum > 1) {
-      // ParallelProcess (bfs.h:158-166)
+      // ParallelProcess (bfs.h:158-166): received vertices join the current level
       MsgView mv = mm.view();
-      BfsApply ap{level, cur, vis, fv.oe_rp, curr_depth};
+      BfsApply ap{cur, vis, fv.oe_rp};
       GL_LAUNCH((k_unpack<ItemU32, BfsApply>), eng.sm_count * 4, kTB, s, mv, ap, eng.ctrl);
       GL_TRY(eng.fetch_ctrl());
       n_f += eng.h_ctrl->aux;
       m_f += eng.h_ctrl->next_edges;
-      visited_cnt += eng.h_ctrl->aux;
       visited_edges += eng.h_ctrl->next_edges;
       GL_TRY(eng.reset_ctrl());
-      GL_CUDA(cudaMemsetAsync(remote + (fv.ivnum >> 5), 0, sizeof(uint32_t) * (words - (fv.ivnum >> 5)), s));
+      GL_CUDA(cudaMemsetAsync(remote, 0, sizeof(uint32_t) * words, s));
     }
-    // direction choice (Beamer-style on edge counts; the reference uses vertex
-    // ratios, bfs.h:171-180 — both only affect speed, never the levels)
-    bool use_pull = false;
-    if (cfg.direction_opt && n_f > 0) {
-      const uint64_t m_total = frag->oe.entries;
-      const uint64_t m_u = m_total > visited_edges ? m_total - visited_edges : 0;
-      if (!pulling) use_pull = m_f > m_u / 14;
-      else use_pull = n_f >= (uint64_t) fv.ivnum / 24;
+    // direction choice; with several fragments every fragment decides on its
+    // own statistics like the reference does (bfs.h:171-180)
+    const uint64_t m_total = frag->oe.entries;
+    const uint64_t m_u = m_total > visited_edges ? m_total - visited_edges : 0;
+    if (!can_pull()) {
+      phase = 0;
+    } else if (phase == 0) {
+      phase = (n_f > 0 && m_f > m_u / 14) ? 1 : 0;
+    } else if (phase == 1) {
+      phase = (n_f >= (uint64_t) fv.ivnum / 24) ? 1 : (fv.fnum > 1 ? 0 : 2);
     }
-    pulling = use_pull;
+    const bool use_pull = phase == 1;
     EdgeRange er{fv.oe_rp, fv.oe_col, nullptr};
     if (!use_pull) {
-      OpBfsPush op{level, vis, nxt, remote, fv.oe_rp, fv.ivnum, next_depth};
+      OpBfsPush op{vis, nxt, remote, fv.oe_rp, fv.ivnum};
       GL_TRY(run_frontier_scan(eng, cur, fv.ivnum, er, op));
     } else {
       static thread_local int gp = 0;
       if (!gp) gp = persistent_grid(k_bfs_pull, eng.sm_count);
       if (fv.ovnum) {
         GL_LAUNCH(k_bfs_pull_outer, eng.sm_count * 8, kTB, s, fv.ovie_rp, fv.ovie_col,
-                  fv.ivnum, fv.ovnum, cur, vis, remote, level, next_depth, eng.ctrl);
+                  fv.ivnum, fv.ovnum, cur, vis, nxt, remote, eng.ctrl);
       }
-      const uint64_t* row_end = fv.fnum > 1 ? fv.oe_split : fv.oe_rp + 1;
-      GL_LAUNCH(k_bfs_pull, gp, kTB, s, fv.oe_rp, row_end, fv.oe_col, fv.ivnum, cur,
-                vis, nxt, frag->nonzero_deg, level, next_depth, eng.ctrl);
+      GL_LAUNCH(k_bfs_pull, gp, kTB, s, pull_args(), cur, vis, nxt, eng.ctrl);
     }
     if (fv.fnum > 1) {
       MsgView mv = mm.view();
@@ -309,18 +630,17 @@ struct BfsApp : gl_app {
     q_touched += c.touched;
     n_f = c.next_count;
     m_f = c.next_edges;
-    visited_cnt += c.next_count;
     visited_edges += c.next_edges;
     if (c.next_count > 0) mm.ForceContinue();
-    curr_depth = next_depth;
-    std::swap(cur, nxt);
-    GL_CUDA(cudaMemsetAsync(nxt, 0, sizeof(uint32_t) * words, s));
+    ++curr_depth;
+    used_lv = curr_depth + 1;
     return GL_OK;
   }
 
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
-    GL_LAUNCH(k_level_to_depth, (fv.ivnum + 255) / 256, 256, eng.stream, level, fv.ivnum, out64);
+    uint32_t nl = std::min<uint32_t>(max_lv, used_lv + 1);
+    GL_LAUNCH(k_depth_from_levels, (fv.ivnum + 255) / 256, 256, eng.stream, lv, (uint32_t) words, nl, fv.ivnum, out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(int64_t) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
     GL_CUDA(cudaStreamSynchronize(eng.stream));
     return GL_OK;

@@ -28,7 +28,7 @@ namespace gl {
 constexpr int kTB = 256;          // threads per CTA
 constexpr int kTileV = 1024;      // vertices per tile (32 bitmap words)
 constexpr uint32_t kHubDeg = 1024;    // rows longer than this go to the hub list
-constexpr uint32_t kHubChunk = 2048;  // entries per hub work item
+constexpr uint32_t kHubChunk = 1024;  // entries per hub work item
 
 // Device control block of one engine (zeroed per superstep by k_ctrl_reset).
 struct ScanCtrl {
@@ -126,150 +126,220 @@ GL_DEV W load_w(const void* w, uint64_t pos) {
 }
 
 // ---------------------------------------------------------------------------
-// k_frontier_scan: fused bitmap -> tile list -> CTA-cooperative edge walk.
+// Frontier scan phase: fused bitmap -> tile list -> CTA-cooperative edge walk.
+// Written as a __device__ phase so that the stand-alone kernel
+// (k_frontier_scan) and the fused whole-query kernels (one cooperative launch
+// per query, grid.sync between supersteps) share the same code.
 // Op requirements:
 //   using Meta = ...; using W = float|double;
 //   static constexpr bool kWeighted;
 //   Meta assign(uint32_t u) const;
 //   void edge(uint32_t u, Meta m, uint32_t v, W w, ScanAcc& acc) const;
 // ---------------------------------------------------------------------------
-template <class Op>
-__global__ void __launch_bounds__(kTB)
-k_frontier_scan(const uint32_t* __restrict__ frontier, uint32_t nverts,
-                EdgeRange er, Op op, ScanCtrl* ctrl, HubItem* hubs,
-                uint32_t hub_cap, uint32_t hub_deg) {
-  using Meta = typename Op::Meta;
-  using W = typename Op::W;
-  __shared__ uint32_t s_v[kTileV];
-  __shared__ uint64_t s_rp[kTileV];
-  __shared__ uint32_t s_pfx[kTileV + 1];
-  __shared__ Meta s_meta[kTileV];
-  __shared__ uint32_t s_warp[kTB / 32 + 1];
-  __shared__ uint32_t s_tile;
+constexpr int kSuperTiles = 8;                    // tiles per ticket
+constexpr int kSuperV = kTileV * kSuperTiles;     // 8192 vertices = 256 words
+constexpr int kMaxTileHubs = 32;                  // long rows emitted cooperatively per tile
 
-  const uint32_t ntiles = (nverts + kTileV - 1) / kTileV;
+template <class Meta>
+struct ScanSmem {
+  uint32_t v[kTileV];
+  uint64_t rp[kTileV];
+  uint32_t pfx[kTileV + 1];
+  Meta meta[kTileV];
+  uint32_t words[kTB];
+  uint32_t warp[kTB / 32 + 1];
+  uint32_t nz[kSuperTiles];
+  uint32_t ticket;
+  uint32_t hubn, hubbase;       // long rows met in the current tile
+  uint32_t hubidx[kMaxTileHubs];
+};
+
+// Draws the next super-tile (8192 bits) and stages its words in shared memory.
+// `word_of(widx)` returns the candidate word.  Returns false when the work is
+// exhausted; sm.nz[k] tells whether sub-tile k has any set bit.
+template <class SM, class WordFn>
+GL_DEV bool next_super_tile(SM& sm, unsigned int* ticket, uint32_t nverts,
+                            WordFn word_of, uint32_t* super_out) {
+  const uint32_t nsuper = (nverts + kSuperV - 1) / kSuperV;
   const uint32_t nwords = (nverts + 31) / 32;
-  ScanAcc acc;
+  for (;;) {
+    if (threadIdx.x == 0) sm.ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t st = sm.ticket;
+    if (st >= nsuper) return false;
+    const uint32_t widx = st * (kSuperV / 32) + threadIdx.x;
+    const uint32_t word = widx < nwords ? word_of(widx) : 0u;
+    sm.words[threadIdx.x] = word;
+    const bool any_w = __any_sync(0xffffffffu, word != 0);
+    if (lane_id() == 0) sm.nz[threadIdx.x >> 5] = any_w;
+    const int any = __syncthreads_or(word != 0);
+    if (any) {
+      *super_out = st;
+      return true;
+    }
+  }
+}
+
+template <class Op>
+GL_DEV void hub_push(uint32_t v, uint64_t b, uint64_t e, ScanCtrl* ctrl,
+                     HubItem* hubs, uint32_t hub_cap) {
+  const uint64_t dg = e - b;
+  uint32_t pieces = (uint32_t) ((dg + kHubChunk - 1) / kHubChunk);
+  uint32_t at = atomicAdd(&ctrl->hub_count, pieces);
+  for (uint32_t p = 0; p < pieces; ++p) {
+    if (at + p < hub_cap) {
+      HubItem h;
+      h.v = v;
+      h.pad = 0;
+      h.begin = b + (uint64_t) p * kHubChunk;
+      h.end = (h.begin + kHubChunk < e) ? h.begin + kHubChunk : e;
+      hubs[at + p] = h;
+    }
+  }
+}
+
+// Walks the edges of the sm.v[0..nf) vertex list CTA-cooperatively.
+template <class Op>
+GL_DEV void walk_tile(ScanSmem<typename Op::Meta>& sm, uint32_t nf, EdgeRange er,
+                      const Op& op, ScanCtrl* ctrl, HubItem* hubs, uint32_t hub_cap,
+                      uint32_t hub_deg, ScanAcc& acc, uint64_t& scanned) {
+  using W = typename Op::W;
+  // row extents; thread t owns list items [4t, 4t+4)
+  uint32_t dsum = 0;
+  uint32_t degs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t i = threadIdx.x * 4 + k;
+    degs[k] = 0;
+    if (i < nf) {
+      uint32_t v = sm.v[i];
+      uint64_t b = er.rp[v], e = er.rp[v + 1];
+      uint64_t dg = e - b;
+      sm.rp[i] = b;
+      sm.meta[i] = op.assign(v);
+      if (dg > hub_deg) {
+        // long row: handed to the hub phase; its work items are written by
+        // the whole CTA below (a single thread emitting 700 items of the
+        // source hub costs tens of microseconds)
+        uint32_t slot = atomicAdd(&sm.hubn, 1u);
+        if (slot < (uint32_t) kMaxTileHubs) sm.hubidx[slot] = i;
+        else hub_push<Op>(v, b, e, ctrl, hubs, hub_cap);
+        dg = 0;
+      }
+      degs[k] = (uint32_t) dg;
+      dsum += degs[k];
+    }
+  }
+  uint32_t total;
+  uint32_t doff = block_excl_scan(dsum, sm.warp, &total);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t i = threadIdx.x * 4 + k;
+    if (i < nf) {
+      sm.pfx[i] = doff;
+      doff += degs[k];
+    }
+  }
+  if (threadIdx.x == 0) sm.pfx[nf] = total;
+  __syncthreads();
+  const uint32_t nh = sm.hubn < (uint32_t) kMaxTileHubs ? sm.hubn : (uint32_t) kMaxTileHubs;
+  if (nh) {  // uniform
+    for (uint32_t h = 0; h < nh; ++h) {
+      const uint32_t i = sm.hubidx[h];
+      const uint32_t v = sm.v[i];
+      const uint64_t b = sm.rp[i], e = er.rp[v + 1];
+      const uint32_t pieces = (uint32_t) ((e - b + kHubChunk - 1) / kHubChunk);
+      if (threadIdx.x == 0) sm.hubbase = atomicAdd(&ctrl->hub_count, pieces);
+      __syncthreads();
+      const uint32_t at = sm.hubbase;
+      for (uint32_t p = threadIdx.x; p < pieces; p += kTB) {
+        if (at + p < hub_cap) {
+          HubItem it;
+          it.v = v;
+          it.pad = 0;
+          it.begin = b + (uint64_t) p * kHubChunk;
+          it.end = (it.begin + kHubChunk < e) ? it.begin + kHubChunk : e;
+          hubs[at + p] = it;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) sm.hubn = 0;
+  }
+  for (uint32_t e0 = 0; e0 < total; e0 += kTB) {
+    uint32_t e = e0 + threadIdx.x;
+    if (e < total) {
+      // largest j with pfx[j] <= e
+      uint32_t lo = 0, hi = nf;
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (sm.pfx[mid] <= e) lo = mid; else hi = mid;
+      }
+      uint64_t pos = sm.rp[lo] + (e - sm.pfx[lo]);
+      uint32_t v = ld_stream_u32(er.col + pos);
+      W w = Op::kWeighted ? load_w<W>(er.w, pos) : (W) 1;
+      op.edge(sm.v[lo], sm.meta[lo], v, w, acc);
+    }
+  }
+  if (threadIdx.x == 0) scanned += total;
+  __syncthreads();
+}
+
+template <class Op>
+GL_DEV void frontier_scan_phase(ScanSmem<typename Op::Meta>& sm,
+                                const uint32_t* __restrict__ frontier,
+                                uint32_t nverts, EdgeRange er, const Op& op,
+                                ScanCtrl* ctrl, HubItem* hubs, uint32_t hub_cap,
+                                uint32_t hub_deg, ScanAcc& acc) {
   uint64_t scanned = 0;
   uint32_t expanded = 0;
-
-  for (;;) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(&ctrl->tile_ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= ntiles) break;
-
-    // 1. expand the tile's set bits: thread t owns bits [4t, 4t+4)
-    const uint32_t widx = tile * (kTileV / 32) + (threadIdx.x >> 3);
-    uint32_t word = widx < nwords ? frontier[widx] : 0u;
-    uint32_t nib = (word >> ((threadIdx.x & 7) * 4)) & 0xFu;
-    uint32_t nf;
-    uint32_t off = block_excl_scan(__popc(nib), s_warp, &nf);
-    if (nf == 0) continue;  // uniform: nf is a CTA-wide value
-    const uint32_t vbase = tile * kTileV + threadIdx.x * 4;
-    while (nib) {
-      uint32_t b = __ffs(nib) - 1;
-      nib &= nib - 1;
-      s_v[off++] = vbase + b;
-    }
-    __syncthreads();
-
-    // 2. row extents; thread t owns list items [4t, 4t+4)
-    uint32_t dsum = 0;
-    uint32_t degs[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint32_t i = threadIdx.x * 4 + k;
-      degs[k] = 0;
-      if (i < nf) {
-        uint32_t v = s_v[i];
-        uint64_t b = er.rp[v], e = er.rp[v + 1];
-        uint64_t dg = e - b;
-        s_rp[i] = b;
-        s_meta[i] = op.assign(v);
-        if (dg > hub_deg) {
-          // cut the hub row into work items for k_hub_scan
-          uint32_t pieces = (uint32_t) ((dg + kHubChunk - 1) / kHubChunk);
-          uint32_t at = atomicAdd(&ctrl->hub_count, pieces);
-          for (uint32_t p = 0; p < pieces; ++p) {
-            if (at + p < hub_cap) {
-              HubItem h;
-              h.v = v;
-              h.pad = 0;
-              h.begin = b + (uint64_t) p * kHubChunk;
-              h.end = (h.begin + kHubChunk < e) ? h.begin + kHubChunk : e;
-              hubs[at + p] = h;
-            }
-          }
-          dg = 0;
-        }
-        degs[k] = (uint32_t) dg;
-        dsum += degs[k];
+  uint32_t st;
+  if (threadIdx.x == 0) sm.hubn = 0;
+  __syncthreads();
+  while (next_super_tile(sm, &ctrl->tile_ticket, nverts,
+                         [&](uint32_t w) { return frontier[w]; }, &st)) {
+    for (int k = 0; k < kSuperTiles; ++k) {
+      if (!sm.nz[k]) continue;  // uniform
+      // expand the sub-tile's set bits: thread t owns bits [4t, 4t+4)
+      uint32_t word = sm.words[k * 32 + (threadIdx.x >> 3)];
+      uint32_t nib = (word >> ((threadIdx.x & 7) * 4)) & 0xFu;
+      uint32_t nf;
+      uint32_t off = block_excl_scan(__popc(nib), sm.warp, &nf);
+      const uint32_t vbase = st * kSuperV + k * kTileV + threadIdx.x * 4;
+      while (nib) {
+        uint32_t b = __ffs(nib) - 1;
+        nib &= nib - 1;
+        sm.v[off++] = vbase + b;
       }
+      __syncthreads();
+      expanded += (threadIdx.x == 0) ? nf : 0;
+      walk_tile<Op>(sm, nf, er, op, ctrl, hubs, hub_cap, hub_deg, acc, scanned);
     }
-    uint32_t total;
-    uint32_t doff = block_excl_scan(dsum, s_warp, &total);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint32_t i = threadIdx.x * 4 + k;
-      if (i < nf) {
-        s_pfx[i] = doff;
-        doff += degs[k];
-      }
-    }
-    if (threadIdx.x == 0) s_pfx[nf] = total;
-    __syncthreads();
-    expanded += (threadIdx.x == 0) ? nf : 0;
-
-    // 3. walk the tile's `total` entries, 256 per sweep
-    for (uint32_t e0 = 0; e0 < total; e0 += kTB) {
-      uint32_t e = e0 + threadIdx.x;
-      if (e < total) {
-        // largest j with s_pfx[j] <= e
-        uint32_t lo = 0, hi = nf;
-        while (hi - lo > 1) {
-          uint32_t mid = (lo + hi) >> 1;
-          if (s_pfx[mid] <= e) lo = mid; else hi = mid;
-        }
-        uint64_t pos = s_rp[lo] + (e - s_pfx[lo]);
-        uint32_t v = ld_stream_u32(er.col + pos);
-        W w = Op::kWeighted ? load_w<W>(er.w, pos) : (W) 1;
-        op.edge(s_v[lo], s_meta[lo], v, w, acc);
-      }
-    }
-    if (threadIdx.x == 0) scanned += total;
-    __syncthreads();
   }
-  flush_acc(acc, ctrl);
   if (threadIdx.x == 0) {
     if (scanned) atomicAdd(&ctrl->scanned, (unsigned long long) scanned);
     if (expanded) atomicAdd(&ctrl->frontier, (unsigned long long) expanded);
   }
 }
 
-// ---------------------------------------------------------------------------
-// k_hub_scan: one work item = <= kHubChunk consecutive entries of one long row.
-// 128-bit coalesced loads of the column tile (and weights).
-// ---------------------------------------------------------------------------
+// Hub phase: one work item = <= kHubChunk consecutive entries of one long row,
+// read with 128-bit coalesced loads.
 template <class Op>
-__global__ void __launch_bounds__(kTB)
-k_hub_scan(EdgeRange er, Op op, ScanCtrl* ctrl, const HubItem* hubs,
-           uint32_t hub_cap) {
+GL_DEV void hub_scan_phase(uint32_t* s_item, EdgeRange er, const Op& op,
+                           ScanCtrl* ctrl, const HubItem* hubs, uint32_t hub_cap,
+                           ScanAcc& acc) {
   using W = typename Op::W;
-  __shared__ uint32_t s_item;
-  ScanAcc acc;
   uint64_t scanned = 0;
   uint32_t n = ctrl->hub_count;
   if (n > hub_cap) n = hub_cap;
   for (;;) {
-    if (threadIdx.x == 0) s_item = atomicAdd(&ctrl->hub_ticket, 1u);
+    if (threadIdx.x == 0) *s_item = atomicAdd(&ctrl->hub_ticket, 1u);
     __syncthreads();
-    uint32_t it = s_item;
+    uint32_t it = *s_item;
     __syncthreads();
     if (it >= n) break;
     HubItem h = hubs[it];
     auto meta = op.assign(h.v);
-    // head: scalar until 16-byte aligned
     uint64_t b = h.begin, e = h.end;
     uint64_t ab = (b + 3) & ~3ull;
     if (ab > e) ab = e;
@@ -298,9 +368,29 @@ k_hub_scan(EdgeRange er, Op op, ScanCtrl* ctrl, const HubItem* hubs,
     }
     if (threadIdx.x == 0) scanned += e - b;
   }
-  flush_acc(acc, ctrl);
   if (threadIdx.x == 0 && scanned)
     atomicAdd(&ctrl->scanned, (unsigned long long) scanned);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kTB)
+k_frontier_scan(const uint32_t* __restrict__ frontier, uint32_t nverts,
+                EdgeRange er, Op op, ScanCtrl* ctrl, HubItem* hubs,
+                uint32_t hub_cap, uint32_t hub_deg) {
+  __shared__ ScanSmem<typename Op::Meta> sm;
+  ScanAcc acc;
+  frontier_scan_phase<Op>(sm, frontier, nverts, er, op, ctrl, hubs, hub_cap, hub_deg, acc);
+  flush_acc(acc, ctrl);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kTB)
+k_hub_scan(EdgeRange er, Op op, ScanCtrl* ctrl, const HubItem* hubs,
+           uint32_t hub_cap) {
+  __shared__ uint32_t s_item;
+  ScanAcc acc;
+  hub_scan_phase<Op>(&s_item, er, op, ctrl, hubs, hub_cap, acc);
+  flush_acc(acc, ctrl);
 }
 
 // ---------------------------------------------------------------------------
@@ -389,92 +479,30 @@ k_queue_scan_warp(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
   if (lane_id() == 0 && s) atomicAdd(&ctrl->scanned, s);
 }
 
-// LB cm / cta: CTA takes kTileV queue entries per ticket; identical walk to
-// k_frontier_scan (cm keeps every row in the tile: hub_deg = UINT32_MAX;
-// cta defers long rows to k_hub_scan).
+// LB cm / cta: a CTA takes kTileV queue entries per ticket and walks them with
+// the same tile walk as the frontier scan (cm keeps every row in the tile:
+// hub_deg = UINT32_MAX; cta defers long rows to k_hub_scan).
 template <class Op>
 __global__ void __launch_bounds__(kTB)
 k_queue_scan_cta(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
                  Op op, ScanCtrl* ctrl, HubItem* hubs, uint32_t hub_cap,
                  uint32_t hub_deg) {
-  using Meta = typename Op::Meta;
-  using W = typename Op::W;
-  __shared__ uint32_t s_v[kTileV];
-  __shared__ uint64_t s_rp[kTileV];
-  __shared__ uint32_t s_pfx[kTileV + 1];
-  __shared__ Meta s_meta[kTileV];
-  __shared__ uint32_t s_warp[kTB / 32 + 1];
-  __shared__ uint32_t s_tile;
+  __shared__ ScanSmem<typename Op::Meta> sm;
   const uint32_t ntiles = (n + kTileV - 1) / kTileV;
   ScanAcc acc;
   uint64_t scanned = 0;
+  if (threadIdx.x == 0) sm.hubn = 0;
+  __syncthreads();
   for (;;) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(&ctrl->tile_ticket, 1u);
+    if (threadIdx.x == 0) sm.ticket = atomicAdd(&ctrl->tile_ticket, 1u);
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = sm.ticket;
     if (tile >= ntiles) break;
     const uint32_t base = tile * kTileV;
     const uint32_t nf = (n - base) < (uint32_t) kTileV ? (n - base) : (uint32_t) kTileV;
-    uint32_t dsum = 0;
-    uint32_t degs[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint32_t i = threadIdx.x * 4 + k;
-      degs[k] = 0;
-      if (i < nf) {
-        uint32_t v = q[base + i];
-        uint64_t b = er.rp[v], e = er.rp[v + 1];
-        uint64_t dg = e - b;
-        s_v[i] = v;
-        s_rp[i] = b;
-        s_meta[i] = op.assign(v);
-        if (dg > hub_deg) {
-          uint32_t pieces = (uint32_t) ((dg + kHubChunk - 1) / kHubChunk);
-          uint32_t at = atomicAdd(&ctrl->hub_count, pieces);
-          for (uint32_t p = 0; p < pieces; ++p) {
-            if (at + p < hub_cap) {
-              HubItem h;
-              h.v = v;
-              h.pad = 0;
-              h.begin = b + (uint64_t) p * kHubChunk;
-              h.end = (h.begin + kHubChunk < e) ? h.begin + kHubChunk : e;
-              hubs[at + p] = h;
-            }
-          }
-          dg = 0;
-        }
-        degs[k] = (uint32_t) dg;
-        dsum += degs[k];
-      }
-    }
-    uint32_t total;
-    uint32_t doff = block_excl_scan(dsum, s_warp, &total);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint32_t i = threadIdx.x * 4 + k;
-      if (i < nf) {
-        s_pfx[i] = doff;
-        doff += degs[k];
-      }
-    }
-    if (threadIdx.x == 0) s_pfx[nf] = total;
+    for (uint32_t i = threadIdx.x; i < nf; i += kTB) sm.v[i] = q[base + i];
     __syncthreads();
-    for (uint32_t e0 = 0; e0 < total; e0 += kTB) {
-      uint32_t e = e0 + threadIdx.x;
-      if (e < total) {
-        uint32_t lo = 0, hi = nf;
-        while (hi - lo > 1) {
-          uint32_t mid = (lo + hi) >> 1;
-          if (s_pfx[mid] <= e) lo = mid; else hi = mid;
-        }
-        uint64_t pos = s_rp[lo] + (e - s_pfx[lo]);
-        uint32_t v = ld_stream_u32(er.col + pos);
-        W w = Op::kWeighted ? load_w<W>(er.w, pos) : (W) 1;
-        op.edge(s_v[lo], s_meta[lo], v, w, acc);
-      }
-    }
-    if (threadIdx.x == 0) scanned += total;
-    __syncthreads();
+    walk_tile<Op>(sm, nf, er, op, ctrl, hubs, hub_cap, hub_deg, acc, scanned);
   }
   flush_acc(acc, ctrl);
   if (threadIdx.x == 0 && scanned)

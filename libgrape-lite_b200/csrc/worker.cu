@@ -71,6 +71,7 @@ void gl_app_config_default(gl_app_config* c) {
   c->pr_delta = 0.85;
   c->max_round = 10;
   c->direction_opt = 1;
+  c->fuse_supersteps = 1;
 }
 
 int gl_app_create(gl_app_t** out, int kind, gl_frag_t* frag, gl_comm_t* comm,
@@ -167,6 +168,7 @@ int gl_app_query(gl_app_t* a, gl_query_stats* stats) {
         stats->step_mode[i] = a->rec.mode[i - 1];
       }
     }
+    a->FillStats(stats);
   }
   return GL_OK;
 }

@@ -34,12 +34,13 @@ def app_available(kind, frag, **cfg):
 
 @pytest.mark.parametrize("directed,name", [(False, "p2p-31-BFS"), (True, "p2p-31-BFS-directed")])
 @pytest.mark.parametrize("dopt", [0, 1])
-def test_bfs_golden(p2p, directed, name, dopt):
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_bfs_golden(p2p, directed, name, dopt, fuse):
     oids, und, dr = p2p
     frag = dr if directed else und
     if directed and dopt:
         pytest.skip("pull needs the transposed adjacency; covered by push")
-    app = app_available("bfs", frag, source_oid=6, direction_opt=dopt)
+    app = app_available("bfs", frag, source_oid=6, direction_opt=dopt, fuse_supersteps=fuse)
     app.query()
     depth = app.result()
     assert np.array_equal(app.result_oids(), oids)
@@ -52,12 +53,13 @@ def test_bfs_golden(p2p, directed, name, dopt):
 
 @pytest.mark.parametrize("scale", [10, 16])
 @pytest.mark.parametrize("dopt", [0, 1])
-def test_bfs_rmat_vs_oracle(scale, dopt):
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_bfs_rmat_vs_oracle(scale, dopt, fuse):
     n, src, dst, _ = rmat_graph(scale, seed=1)
     g = pyoracle.Graph(n, src, dst, None)
     frag = pkg().Fragment.rmat(scale, 16, seed=1)
     for source in (g.max_degree_vertex(), 0, n - 1):
-        app = app_available("bfs", frag, source_oid=int(source), direction_opt=dopt)
+        app = app_available("bfs", frag, source_oid=int(source), direction_opt=dopt, fuse_supersteps=fuse)
         st = app.query()
         want, _ = g.bfs(source)
         assert np.array_equal(app.result(), want)
