@@ -99,8 +99,11 @@ k_bfs_hub_nbr(const uint64_t* __restrict__ rp, const uint64_t* __restrict__ row_
 // Pull step over the inner vertices (bfs.h:239-259) as a phase shared by the
 // stand-alone kernel and the fused whole-query kernel.
 // ---------------------------------------------------------------------------
+constexpr uint32_t kPullSerialCap = 8;   // row entries a single thread probes
 struct PullSmem {
   uint32_t v[kTileV];
+  uint32_t lng[kTileV];   // candidates whose row is longer than the cap
+  uint32_t nlong;
   uint32_t found[kTileV / 32];
   uint32_t words[kTB];
   uint32_t warp[kTB / 32 + 1];
@@ -129,6 +132,8 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
   uint64_t scanned = 0;
   uint32_t cand = 0;
   uint32_t st;
+  if (threadIdx.x == 0) sm.nlong = 0;
+  __syncthreads();
   while (next_super_tile(sm, &ctrl->tile_ticket, a.ivnum,
                          [&](uint32_t w) { return a.nz[w] & ~vis[w]; }, &st)) {
     const uint32_t word = sm.words[threadIdx.x];
@@ -139,19 +144,28 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
     uint32_t res = 0;
     if (word) {
       const uint4* hp = (const uint4*) (a.hub_nbr + vbase);
-#pragma unroll 4
+      // branch-free: every probe is an unconditional load (index 0 when the
+      // lane is not a candidate) so that the loads of one iteration are all
+      // in flight together instead of forming a chain of dependent branches
+#pragma unroll 2
       for (int j = 0; j < 8; ++j) {
         const uint32_t nib = (word >> (4 * j)) & 0xFu;
-        if (nib) {
-          const uint4 h = hp[j];
-          // kInfU32 = the row has no inner neighbour
-          uint32_t r = 0;
-          if ((nib & 1u) && h.x != kInfU32 && bit_test(cur, h.x)) r |= 1u;
-          if ((nib & 2u) && h.y != kInfU32 && bit_test(cur, h.y)) r |= 2u;
-          if ((nib & 4u) && h.z != kInfU32 && bit_test(cur, h.z)) r |= 4u;
-          if ((nib & 8u) && h.w != kInfU32 && bit_test(cur, h.w)) r |= 8u;
-          res |= r << (4 * j);
-        }
+        uint4 h = make_uint4(kInfU32, kInfU32, kInfU32, kInfU32);
+        if (nib) h = hp[j];
+        const bool c0 = (nib & 1u) && h.x != kInfU32;
+        const bool c1 = (nib & 2u) && h.y != kInfU32;
+        const bool c2 = (nib & 4u) && h.z != kInfU32;
+        const bool c3 = (nib & 8u) && h.w != kInfU32;
+        const uint32_t i0 = c0 ? h.x : 0u, i1 = c1 ? h.y : 0u;
+        const uint32_t i2 = c2 ? h.z : 0u, i3 = c3 ? h.w : 0u;
+        const uint32_t w0 = cur[i0 >> 5], w1 = cur[i1 >> 5];
+        const uint32_t w2 = cur[i2 >> 5], w3 = cur[i3 >> 5];
+        uint32_t r = 0;
+        r |= (c0 && ((w0 >> (i0 & 31)) & 1u)) ? 1u : 0u;
+        r |= (c1 && ((w1 >> (i1 & 31)) & 1u)) ? 2u : 0u;
+        r |= (c2 && ((w2 >> (i2 & 31)) & 1u)) ? 4u : 0u;
+        r |= (c3 && ((w3 >> (i3 & 31)) & 1u)) ? 8u : 0u;
+        res |= r << (4 * j);
       }
       scanned += __popc(word);
     }
@@ -171,14 +185,18 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
       }
       __syncthreads();
       const uint32_t nc = (total - base) < (uint32_t) kTileV ? (total - base) : (uint32_t) kTileV;
+      // 2a: every thread probes at most kPullSerialCap entries of its rows;
+      // longer rows go to the warp-cooperative pass so that one unlucky
+      // thread cannot stall the CTA behind a chain of dependent loads
       for (uint32_t i = threadIdx.x; i < nc; i += kTB) {
         const uint32_t v = sm.v[i];
         const uint64_t b = a.rp[v];
         const uint32_t len = (uint32_t) (a.row_end[v] - b);
         const uint32_t* row = a.col + b;
+        const uint32_t lim = len < kPullSerialCap ? len : kPullSerialCap;
         bool found = false;
         uint32_t p = 0;
-        for (; p < len; ++p) {
+        for (; p < lim; ++p) {
           if (bit_test(cur, row[p])) {
             found = true;
             ++p;
@@ -187,8 +205,34 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
         }
         scanned += p;
         if (found) atomicOr(&sm.words[(v >> 5) - st * (kSuperV / 32)], 1u << (v & 31));
+        else if (len > kPullSerialCap) sm.lng[atomicAdd(&sm.nlong, 1u)] = v;
       }
       __syncthreads();
+      // 2b: one warp per long row, 32 entries per step
+      const uint32_t nl = sm.nlong;
+      for (uint32_t i = threadIdx.x >> 5; i < nl; i += kTB / 32) {
+        const uint32_t v = sm.lng[i];
+        const uint64_t b = a.rp[v];
+        const uint32_t len = (uint32_t) (a.row_end[v] - b);
+        const uint32_t* row = a.col + b;
+        bool hit = false;
+        uint32_t p = kPullSerialCap;
+        for (; p < len; p += 32) {
+          const uint32_t q = p + lane_id();
+          const bool h = q < len && bit_test(cur, row[q]);
+          if (__any_sync(0xffffffffu, h)) {
+            hit = true;
+            p += 32;
+            break;
+          }
+        }
+        if (lane_id() == 0) {
+          scanned += (p < len ? p : len) - kPullSerialCap;
+          if (hit) atomicOr(&sm.words[(v >> 5) - st * (kSuperV / 32)], 1u << (v & 31));
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) sm.nlong = 0;
     }
     if (total == 0) __syncthreads();  // sm.words zeroing vs. the next ticket
     const uint32_t found_w = res | sm.words[threadIdx.x];
