@@ -133,15 +133,8 @@ def run_gpu(args):
 
     comm = None
     if world > 1:
-        def allreduce(arr, op):
-            t = torch.from_numpy(arr).cuda()
-            dist.all_reduce(t, op={0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX}[op])
-            arr[:] = t.cpu().numpy()
-        item = 16
-        comm = pkg.Comm(rank, world, allreduce, landing_bytes=item * (frag.ivnum + 1024))
-        handles = [None] * world
-        dist.all_gather_object(handles, comm.export())
-        comm.open(handles)
+        gdist = importlib.import_module("libgrape-lite_b200.dist")
+        comm = gdist.make_comm(rank, world, frag.ivnum, item_bytes=16)
 
     # source = max-degree vertex of the whole graph, ties -> smallest oid
     lid, deg = frag.max_degree_vertex()
@@ -246,9 +239,26 @@ def run_gpu(args):
     agg_fr /= max(cnt, 1)
     dom = int(np.argmax(agg_ms))
     touched_dom = last[7] * (agg_ent[dom] / max(sum(agg_ent), 1.0))
-    b_alg = alg_bytes(args.app, agg_ent[dom], agg_fr[dom], touched_dom, weighted)
-    achieved = b_alg / (agg_ms[dom] * 1e-3) / 1e9 if agg_ms[dom] > 0 else 0.0
     whole_balg = alg_bytes(args.app, last[5], last[6], last[7], weighted)
+    fused_query = args.app == "bfs" and world == 1 and not args.no_fuse
+    if fused_query:
+        # the whole query is ONE launch (k_bfs_fused): the dominant kernel is the step
+        dom_name = "k_bfs_fused"
+        b_alg = whole_balg
+        dom_ms = ms_per_step
+    else:
+        dom_name = {0: "k_frontier_scan+k_hub_scan", 1: "k_bfs_pull", 2: "dense scan"}[int(last[4][dom])]
+        b_alg = alg_bytes(args.app, agg_ent[dom], agg_fr[dom], touched_dom, weighted)
+        dom_ms = float(agg_ms[dom])
+    achieved = b_alg / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = dom_name if dom_name in tj else None
+        if key and args.app == "bfs" and scale == 24:
+            traffic = tj[key]["bytes"]
+    except Exception:
+        pass
 
     line = None
     if rank == 0:
@@ -278,9 +288,9 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "superstep %d (%s)" % (dom, {0: "k_frontier_scan+k_hub_scan", 1: "k_bfs_pull", 2: "dense"}[int(last[4][dom])]),
-                         "alg_bytes_per_launch": b_alg, "ms_per_launch": float(agg_ms[dom]),
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": dom_name if fused_query else "superstep %d (%s)" % (dom, dom_name),
+                         "alg_bytes_per_launch": b_alg, "ms_per_launch": dom_ms,
                          "whole_query_alg_bytes": whole_balg,
                          "whole_query_gbs": whole_balg / (ms_per_step * 1e-3) / 1e9},
         }
