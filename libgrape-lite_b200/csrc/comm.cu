@@ -24,7 +24,80 @@ __global__ void k_publish_counts(uint32_t fnum, uint32_t fid,
   }
   __threadfence_system();
 }
+// One block, one thread per peer: publish my contribution to every peer, wait
+// for every peer's contribution of the same sequence number, reduce.
+// With peer_count != nullptr it first publishes this round's item counts
+// (FinishARound) and adds their total to i1, so that a round closes with ONE
+// kernel and ONE stream synchronisation.
+__global__ void k_peer_allreduce(uint32_t fnum, uint32_t fid, PeerSlot* const* my_slot_at_peer,
+                                 const PeerSlot* local_slots, unsigned long long tag,
+                                 long long i0, long long i1, double d0, int op,
+                                 uint32_t* const* peer_count, uint32_t* send_count,
+                                 uint32_t* h_counts, PeerSlot* h_out) {
+  __shared__ long long s_i0[GL_MAX_FNUM], s_i1[GL_MAX_FNUM];
+  __shared__ double s_d0[GL_MAX_FNUM];
+  __shared__ unsigned int s_total;
+  const uint32_t p = threadIdx.x;
+  if (p == 0) s_total = 0;
+  __syncthreads();
+  if (peer_count && p < fnum) {
+    uint32_t c = send_count[p];
+    if (p != fid) {
+      *peer_count[p] = c;  // NVLink peer store
+      atomicAdd(&s_total, c);
+    }
+    h_counts[p] = c;
+    send_count[p] = 0;
+  }
+  __syncthreads();
+  i1 += (long long) s_total;
+  if (p < fnum) {
+    PeerSlot* dst = my_slot_at_peer[p];        // peer p's header, slot [me] (p == me: local)
+    dst->i0 = i0;
+    dst->i1 = i1;
+    dst->d0 = d0;
+    __threadfence_system();
+    *(volatile unsigned long long*) &dst->tag = tag;
+    // wait for peer p's contribution in MY header, slot [p]
+    const volatile PeerSlot* src = local_slots + p;
+    while (src->tag != tag) __nanosleep(64);
+    __threadfence_system();
+    s_i0[p] = src->i0;
+    s_i1[p] = src->i1;
+    s_d0[p] = src->d0;
+  }
+  __syncthreads();
+  if (p == 0) {
+    long long a = s_i0[0], b = s_i1[0];
+    double c = s_d0[0];
+    for (uint32_t q = 1; q < fnum; ++q) {
+      if (op == 0) { a += s_i0[q]; b += s_i1[q]; c += s_d0[q]; }
+      else if (op == 1) { a = a < s_i0[q] ? a : s_i0[q]; b = b < s_i1[q] ? b : s_i1[q]; c = c < s_d0[q] ? c : s_d0[q]; }
+      else { a = a > s_i0[q] ? a : s_i0[q]; b = b > s_i1[q] ? b : s_i1[q]; c = c > s_d0[q] ? c : s_d0[q]; }
+    }
+    h_out->i0 = a;
+    h_out->i1 = b;
+    h_out->d0 = c;
+    h_out->tag = tag;
+  }
+  (void) fid;
+}
 }  // namespace
+
+int MessageManager::PeerAllReduce(cudaStream_t s, long long* i0, long long* i1, double* d0, int op) {
+  const unsigned long long tag = ++comm->seq_base;
+  const int par = (int) (tag & 1);
+  const PeerSlot* local = (const PeerSlot*) (comm->local_base + GL_COMM_SLOT_OFF) + (size_t) par * GL_MAX_FNUM;
+  k_peer_allreduce<<<1, GL_MAX_FNUM, 0, s>>>(fnum, fid, d_peer_slot[par], local, tag, *i0, *i1, *d0, op,
+                                             nullptr, nullptr, nullptr, h_result);
+  GL_COUNT_LAUNCH();
+  GL_CUDA(cudaGetLastError());
+  GL_CUDA(cudaStreamSynchronize(s));
+  *i0 = h_result->i0;
+  *i1 = h_result->i1;
+  *d0 = h_result->d0;
+  return GL_OK;
+}
 
 int MessageManager::Init(gl_comm* c, const gl_frag_view& fv, uint32_t item_bytes_) {
   comm = c;
@@ -41,6 +114,7 @@ int MessageManager::Init(gl_comm* c, const gl_frag_view& fv, uint32_t item_bytes
   GL_CUDA(cudaMalloc(&d_send_count, sizeof(uint32_t) * fnum));
   GL_CUDA(cudaMemset(d_send_count, 0, sizeof(uint32_t) * fnum));
   GL_CUDA(cudaMallocHost(&h_send_count, sizeof(uint32_t) * (fnum + 1)));
+  GL_CUDA(cudaMallocHost(&h_result, sizeof(PeerSlot)));
   for (int par = 0; par < 2; ++par) {
     std::vector<char*> send(fnum);
     std::vector<const char*> recv(fnum);
@@ -54,6 +128,11 @@ int MessageManager::Init(gl_comm* c, const gl_frag_view& fv, uint32_t item_bytes
       recv[p] = c->local_base + GL_COMM_HEADER +
                 ((size_t) par * fnum + p) * c->landing_bytes;
     }
+    std::vector<PeerSlot*> ps(fnum);
+    for (uint32_t p = 0; p < fnum; ++p)
+      ps[p] = (PeerSlot*) (c->peer_base[p] + GL_COMM_SLOT_OFF) + (size_t) par * GL_MAX_FNUM + fid;
+    GL_CUDA(cudaMalloc(&d_peer_slot[par], sizeof(PeerSlot*) * fnum));
+    GL_CUDA(cudaMemcpy(d_peer_slot[par], ps.data(), sizeof(PeerSlot*) * fnum, cudaMemcpyHostToDevice));
     GL_CUDA(cudaMalloc(&d_send_slot[par], sizeof(char*) * fnum));
     GL_CUDA(cudaMalloc(&d_recv_slot[par], sizeof(char*) * fnum));
     GL_CUDA(cudaMalloc(&d_peer_count[par], sizeof(uint32_t*) * fnum));
@@ -69,12 +148,16 @@ void MessageManager::Destroy() {
     if (d_send_slot[par]) cudaFree(d_send_slot[par]);
     if (d_recv_slot[par]) cudaFree((void*) d_recv_slot[par]);
     if (d_peer_count[par]) cudaFree(d_peer_count[par]);
+    if (d_peer_slot[par]) cudaFree(d_peer_slot[par]);
+    d_peer_slot[par] = nullptr;
     d_send_slot[par] = nullptr;
     d_recv_slot[par] = nullptr;
     d_peer_count[par] = nullptr;
   }
   if (d_send_count) cudaFree(d_send_count);
   if (h_send_count) cudaFreeHost(h_send_count);
+  if (h_result) cudaFreeHost(h_result);
+  h_result = nullptr;
   d_send_count = nullptr;
   h_send_count = nullptr;
 }
@@ -98,7 +181,8 @@ MsgView MessageManager::view() const {
   return v;
 }
 
-int MessageManager::StartARound(cudaStream_t) {
+int MessageManager::StartARound(cudaStream_t s) {
+  stream_for_collectives = s;
   force_continue = false;
   return GL_OK;
 }
@@ -108,10 +192,24 @@ int MessageManager::FinishARound(cudaStream_t s) {
   int64_t vote[2] = {force_continue ? 1 : 0, 0};
   if (fnum > 1) {
     int par = round & 1;
-    k_publish_counts<<<1, GL_MAX_FNUM, 0, s>>>(fnum, fid, d_peer_count[par], d_send_count, h_send_count);
-    GL_COUNT_LAUNCH();
-    GL_CUDA(cudaGetLastError());
-    GL_CUDA(cudaStreamSynchronize(s));
+    if (use_peer_barrier) {
+      // publish counts + barrier + termination vote: one kernel, one sync
+      const unsigned long long tag = ++comm->seq_base;
+      const int bp = (int) (tag & 1);
+      const PeerSlot* local = (const PeerSlot*) (comm->local_base + GL_COMM_SLOT_OFF) + (size_t) bp * GL_MAX_FNUM;
+      k_peer_allreduce<<<1, GL_MAX_FNUM, 0, s>>>(fnum, fid, d_peer_slot[bp], local, tag, (long long) vote[0], 0ll,
+                                                 0.0, 0, d_peer_count[par], d_send_count, h_send_count, h_result);
+      GL_COUNT_LAUNCH();
+      GL_CUDA(cudaGetLastError());
+      GL_CUDA(cudaStreamSynchronize(s));
+      vote[0] = h_result->i0;
+      vote[1] = h_result->i1;
+    } else {
+      k_publish_counts<<<1, GL_MAX_FNUM, 0, s>>>(fnum, fid, d_peer_count[par], d_send_count, h_send_count);
+      GL_COUNT_LAUNCH();
+      GL_CUDA(cudaGetLastError());
+      GL_CUDA(cudaStreamSynchronize(s));
+    }
     uint64_t sent = 0;
     for (uint32_t p = 0; p < fnum; ++p)
       if (p != fid) {
@@ -122,8 +220,10 @@ int MessageManager::FinishARound(cudaStream_t s) {
         sent += h_send_count[p];
       }
     bytes_sent += sent * item_bytes;
-    vote[1] = (int64_t) sent;
-    GL_TRY(AllReduceI64(vote, 2, 0));
+    if (!use_peer_barrier) {
+      vote[1] = (int64_t) sent;
+      GL_TRY(AllReduceI64(vote, 2, 0));
+    }
   } else {
     GL_CUDA(cudaStreamSynchronize(s));
   }
@@ -147,6 +247,11 @@ int MessageManager::AllReduceI64(int64_t* v, int n, int op) {
 }
 int MessageManager::AllReduceF64(double* v, int n, int op) {
   if (fnum == 1) return GL_OK;
+  if (use_peer_barrier && n == 1 && comm && comm->opened) {
+    long long a = 0, b = 0;
+    cudaStream_t s0 = stream_for_collectives;
+    return PeerAllReduce(s0, &a, &b, v, op);
+  }
   if (!comm || !comm->allreduce) {
     set_error("communicator has no allreduce callback");
     return GL_ERR_COMM;

@@ -19,7 +19,16 @@
 #include "common.cuh"
 
 constexpr uint32_t GL_MAX_FNUM = 64;
-constexpr size_t GL_COMM_HEADER = 4096;  // counts[2][GL_MAX_FNUM] u32 + flags
+// Header of a landing area: item counts + the peer-barrier slots.
+//   [0, 512)      uint32 counts[2][GL_MAX_FNUM]
+//   [1024, 5120)  PeerSlot slots[2][GL_MAX_FNUM]   (32 B each)
+constexpr size_t GL_COMM_HEADER = 8192;
+constexpr size_t GL_COMM_SLOT_OFF = 1024;
+struct PeerSlot {            // one rank's contribution to a collective
+  unsigned long long tag;    // sequence number, written last (release)
+  long long i0, i1;
+  double d0;
+};
 
 struct gl_comm {
   uint32_t fid = 0, fnum = 1;
@@ -29,6 +38,7 @@ struct gl_comm {
   char* local_base = nullptr;
   std::vector<char*> peer_base;  // [fnum]; peer_base[fid] == local_base
   bool opened = false;
+  unsigned long long seq_base = 0;  // last collective sequence number used on this communicator
   size_t total_bytes() const {
     return GL_COMM_HEADER + 2 * (size_t) fnum * landing_bytes;
   }
@@ -79,6 +89,17 @@ struct MessageManager {
   // all-reduce helpers (cuda::Communicator::Sum/Min/Max, communicator.h:41-84)
   int AllReduceI64(int64_t* v, int n, int op);
   int AllReduceF64(double* v, int n, int op);
+  // Device-side collective over NVLink peer memory: every rank stores its
+  // contribution into every peer's header slot and spins until all peers'
+  // slots carry this collective's sequence number.  Sum of (i0, i1, d0) in
+  // fid order => bit-identical on all ranks.  Also a barrier: it is issued
+  // after the round's peer stores on the same stream.
+  int PeerAllReduce(cudaStream_t s, long long* i0, long long* i1, double* d0, int op);
+  bool use_peer_barrier = true;
+  cudaStream_t stream_for_collectives = nullptr;
+  unsigned long long seq = 0;
+  PeerSlot** d_peer_slot[2] = {nullptr, nullptr};  // [parity][fnum] my slot at peer p
+  PeerSlot* h_result = nullptr;                    // pinned
 };
 
 #ifdef __CUDACC__
