@@ -344,3 +344,58 @@ class App:
     def __del__(self):
         if getattr(self, "h", None) and _LIB is not None:
             self.close()
+
+
+class DeviceArray:
+    """Tiny device buffer helper for the engine-primitive tests."""
+
+    def __init__(self, host=None, nbytes=None):
+        self.ptr = C.c_void_p()
+        self.nbytes = host.nbytes if host is not None else nbytes
+        check(lib().gl_dev_alloc(C.byref(self.ptr), C.c_size_t(max(self.nbytes, 16))))
+        if host is not None:
+            self.upload(host)
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host)
+        check(lib().gl_dev_h2d(self.ptr, _p(host), C.c_size_t(host.nbytes)))
+
+    def download(self, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        check(lib().gl_dev_d2h(_p(out), self.ptr, C.c_size_t(out.nbytes)))
+        return out
+
+    def fill(self, byte):
+        check(lib().gl_dev_memset(self.ptr, int(byte), C.c_size_t(self.nbytes)))
+
+    def free(self):
+        if self.ptr:
+            lib().gl_dev_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and self.ptr.value and _LIB is not None:
+            self.free()
+
+
+OPS = {"bfs_level": 0, "min_relax_u32": 1, "min_relax_f32": 2, "add_scatter_f64": 3, "count": 4}
+
+
+def edge_scan_queue(frag, queue_dev, n, op, lb, state=None, state2=None, out_bitmap=None, depth=0,
+                    use_weight=0):
+    """ForEachOutgoingEdge(WorkSourceArray(queue, n), op, lb) -> entries scanned."""
+    o = EdgeOp(OPS[op] if isinstance(op, str) else op,
+               state.ptr if state is not None else None,
+               state2.ptr if state2 is not None else None,
+               out_bitmap.ptr if out_bitmap is not None else None, depth, use_weight)
+    scanned = C.c_uint64()
+    lbv = GL_LB[lb] if isinstance(lb, str) else lb
+    check(lib().gl_edge_scan_queue(frag.h, None, queue_dev.ptr, C.c_uint32(n), C.byref(o), lbv,
+                                   C.byref(scanned)))
+    return scanned.value
+
+
+def compact_bitmap(bitmap_dev, n_bits, queue_dev):
+    cnt = C.c_uint32()
+    check(lib().gl_compact_bitmap(None, bitmap_dev.ptr, C.c_uint32(n_bits), queue_dev.ptr, C.byref(cnt)))
+    return cnt.value
