@@ -1,0 +1,6 @@
+// Drop-in replacement for the reference's grape/cuda/utils/dev_utils.h: same include path,
+// same public names, implemented on the B200 engine (see b200_compat.h).
+#ifndef GRAPE_B200_COMPAT_UTILS_DEV_UTILS_H
+#define GRAPE_B200_COMPAT_UTILS_DEV_UTILS_H
+#include "grape/cuda/b200_compat.h"
+#endif

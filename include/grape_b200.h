@@ -179,6 +179,7 @@ typedef struct {
                                   (outer_vertices_of_frag_)                   */
   const int64_t* inner_oids;   /* may be NULL (oid = oid_base + lid)          */
   int64_t oid_base;
+  uint64_t oe_num, ie_num;     /* CSR entries behind oe_col / ie_col          */
 } gl_frag_view;
 int gl_frag_view_get(const gl_frag_t*, gl_frag_view* out);
 

@@ -393,20 +393,30 @@ k_hub_scan(EdgeRange er, Op op, ScanCtrl* ctrl, const HubItem* hubs,
   flush_acc(acc, ctrl);
 }
 
+// Work sources (grape/cuda/utils/work_source.h): item i -> vertex id
+struct ArraySrc {
+  const uint32_t* q;
+  GL_DEV uint32_t operator()(uint32_t i) const { return q[i]; }
+};
+struct RangeSrc {
+  uint32_t start;
+  GL_DEV uint32_t operator()(uint32_t i) const { return start + i; }
+};
+
 // ---------------------------------------------------------------------------
-// Queue-driven variants (WorkSourceArray): the LB modes of the C ABI.
+// Queue-driven variants (WorkSourceArray / WorkSourceRange): the LB modes.
 // ---------------------------------------------------------------------------
 // LB none: thread per vertex, serial row walk (LBNONE, :621-646)
-template <class Op>
+template <class Op, class Src = ArraySrc>
 __global__ void __launch_bounds__(kTB)
-k_queue_scan_none(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
+k_queue_scan_none(Src q, uint32_t n, EdgeRange er,
                   Op op, ScanCtrl* ctrl) {
   using W = typename Op::W;
   ScanAcc acc;
   uint64_t scanned = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += gridDim.x * blockDim.x) {
-    uint32_t u = q[i];
+    uint32_t u = q(i);
     auto m = op.assign(u);
     uint64_t b = er.rp[u], e = er.rp[u + 1];
     for (uint64_t p = b; p < e; ++p) {
@@ -422,9 +432,9 @@ k_queue_scan_none(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
 
 // LB wm: a warp takes 32 queue entries, scans their degrees and the lanes
 // sweep the concatenated edges (LBWARP, :773-845)
-template <class Op>
+template <class Op, class Src = ArraySrc>
 __global__ void __launch_bounds__(kTB)
-k_queue_scan_warp(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
+k_queue_scan_warp(Src q, uint32_t n, EdgeRange er,
                   Op op, ScanCtrl* ctrl) {
   using W = typename Op::W;
   using Meta = typename Op::Meta;
@@ -439,7 +449,7 @@ k_queue_scan_warp(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
     uint32_t dg = 0;
     Meta m = Meta();
     if (i < n) {
-      u = q[i];
+      u = q(i);
       b = er.rp[u];
       uint64_t d64 = er.rp[u + 1] - b;
       dg = d64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t) d64;
@@ -482,9 +492,9 @@ k_queue_scan_warp(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
 // LB cm / cta: a CTA takes kTileV queue entries per ticket and walks them with
 // the same tile walk as the frontier scan (cm keeps every row in the tile:
 // hub_deg = UINT32_MAX; cta defers long rows to k_hub_scan).
-template <class Op>
+template <class Op, class Src = ArraySrc>
 __global__ void __launch_bounds__(kTB)
-k_queue_scan_cta(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
+k_queue_scan_cta(Src q, uint32_t n, EdgeRange er,
                  Op op, ScanCtrl* ctrl, HubItem* hubs, uint32_t hub_cap,
                  uint32_t hub_deg) {
   __shared__ ScanSmem<typename Op::Meta> sm;
@@ -500,7 +510,7 @@ k_queue_scan_cta(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
     if (tile >= ntiles) break;
     const uint32_t base = tile * kTileV;
     const uint32_t nf = (n - base) < (uint32_t) kTileV ? (n - base) : (uint32_t) kTileV;
-    for (uint32_t i = threadIdx.x; i < nf; i += kTB) sm.v[i] = q[base + i];
+    for (uint32_t i = threadIdx.x; i < nf; i += kTB) sm.v[i] = q(base + i);
     __syncthreads();
     walk_tile<Op>(sm, nf, er, op, ctrl, hubs, hub_cap, hub_deg, acc, scanned);
   }
@@ -512,9 +522,9 @@ k_queue_scan_cta(const uint32_t* __restrict__ q, uint32_t n, EdgeRange er,
 // LB strict: exact edge balance.  pfx[i] = exclusive prefix of the queue's
 // degrees (pfx[n] = total); CTA c owns entries [c*per, (c+1)*per)
 // (LBSTRICT :881-979, without the host-side sorted_search / allocations).
-template <class Op>
+template <class Op, class Src = ArraySrc>
 __global__ void __launch_bounds__(kTB)
-k_queue_scan_strict(const uint32_t* __restrict__ q, uint32_t n,
+k_queue_scan_strict(Src q, uint32_t n,
                     const uint64_t* __restrict__ pfx, EdgeRange er, Op op,
                     ScanCtrl* ctrl) {
   using W = typename Op::W;
@@ -531,7 +541,7 @@ k_queue_scan_strict(const uint32_t* __restrict__ q, uint32_t n,
       uint32_t mid = (lo + hi) >> 1;
       if (pfx[mid] <= e) lo = mid; else hi = mid;
     }
-    uint32_t u = q[lo];
+    uint32_t u = q(lo);
     uint64_t pos = er.rp[u] + (e - pfx[lo]);
     W w = Op::kWeighted ? load_w<W>(er.w, pos) : (W) 1;
     op.edge(u, op.assign(u), ld_stream_u32(er.col + pos), w, acc);
@@ -541,10 +551,13 @@ k_queue_scan_strict(const uint32_t* __restrict__ q, uint32_t n,
     atomicAdd(&ctrl->scanned, (unsigned long long) (hi_e - lo_e));
 }
 
-static __global__ void k_queue_degrees(const uint32_t* q, uint32_t n,
-                                const uint64_t* rp, uint64_t* deg) {
+template <class Src = ArraySrc>
+__global__ void k_queue_degrees(Src q, uint32_t n, const uint64_t* rp, uint64_t* deg) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) deg[i] = rp[q[i] + 1] - rp[q[i]];
+  if (i < n) {
+    uint32_t u = q(i);
+    deg[i] = rp[u + 1] - rp[u];
+  }
   if (i == n) deg[i] = 0;
 }
 

@@ -649,6 +649,8 @@ void frag_fill_view(const gl_frag* f, gl_frag_view* v) {
   v->outer_range = f->outer_range;
   v->inner_oids = f->inner_oids;
   v->oid_base = f->oid_base;
+  v->oe_num = f->oe.entries;
+  v->ie_num = f->ie.entries;
 }
 
 }  // namespace gl

@@ -133,12 +133,12 @@ int scan_queue(const gl_frag* f, cudaStream_t s, const uint32_t* q, uint32_t n,
     switch (lb) {
       case GL_LB_NONE: {
         int g = std::min<int>(persistent_grid(k_queue_scan_none<Op>, di->sm_count), (int) ((n + kTB - 1) / kTB));
-        GL_LAUNCH(k_queue_scan_none<Op>, g, kTB, s, q, n, er, op, ps.ctrl);
+        GL_LAUNCH(k_queue_scan_none<Op>, g, kTB, s, ArraySrc{q}, n, er, op, ps.ctrl);
         break;
       }
       case GL_LB_WM: {
         int g = std::min<int>(persistent_grid(k_queue_scan_warp<Op>, di->sm_count), (int) ((n + kTB - 1) / kTB));
-        GL_LAUNCH(k_queue_scan_warp<Op>, g, kTB, s, q, n, er, op, ps.ctrl);
+        GL_LAUNCH(k_queue_scan_warp<Op>, g, kTB, s, ArraySrc{q}, n, er, op, ps.ctrl);
         break;
       }
       case GL_LB_CM:
@@ -148,7 +148,7 @@ int scan_queue(const gl_frag* f, cudaStream_t s, const uint32_t* q, uint32_t n,
         // grid-wide work items (k_hub_scan)
         uint32_t hub_deg = lb == GL_LB_CTA ? kHubDeg : 0xFFFFFFFFu;
         int g = std::min<int>(persistent_grid(k_queue_scan_cta<Op>, di->sm_count), (int) ((n + kTileV - 1) / kTileV));
-        GL_LAUNCH(k_queue_scan_cta<Op>, g, kTB, s, q, n, er, op, ps.ctrl, ps.hubs, ps.hub_cap, hub_deg);
+        GL_LAUNCH(k_queue_scan_cta<Op>, g, kTB, s, ArraySrc{q}, n, er, op, ps.ctrl, ps.hubs, ps.hub_cap, hub_deg);
         if (lb == GL_LB_CTA) {
           int g2 = persistent_grid(k_hub_scan<Op>, di->sm_count);
           GL_LAUNCH(k_hub_scan<Op>, g2, kTB, s, er, op, ps.ctrl, ps.hubs, ps.hub_cap);
@@ -156,10 +156,10 @@ int scan_queue(const gl_frag* f, cudaStream_t s, const uint32_t* q, uint32_t n,
         break;
       }
       case GL_LB_STRICT: {
-        GL_LAUNCH(k_queue_degrees, (n + 1 + 255) / 256, 256, s, q, n, f->oe.rp, ps.deg);
+        GL_LAUNCH(k_queue_degrees<ArraySrc>, (n + 1 + 255) / 256, 256, s, ArraySrc{q}, n, f->oe.rp, ps.deg);
         GL_CUDA(cub::DeviceScan::ExclusiveSum(ps.scan_tmp, ps.scan_bytes, ps.deg, ps.pfx, (int) (n + 1), s));
         int g = persistent_grid(k_queue_scan_strict<Op>, di->sm_count);
-        GL_LAUNCH(k_queue_scan_strict<Op>, g, kTB, s, q, n, ps.pfx, er, op, ps.ctrl);
+        GL_LAUNCH(k_queue_scan_strict<Op>, g, kTB, s, ArraySrc{q}, n, ps.pfx, er, op, ps.ctrl);
         break;
       }
       default:

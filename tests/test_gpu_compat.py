@@ -1,0 +1,80 @@
+"""GPU: the reference's UNCHANGED GPU app sources
+(examples/analytical_apps/cuda/{bfs,sssp,wcc,pagerank}/*.h), compiled against
+this repo's drop-in grape/cuda/** headers (compat/), reproduce the reference's
+golden files — the reference's own GPU test matrix (misc/cuda_app_tests.sh:69-132:
+apps x --lb modes, ExactVerify / EpsVerify / WCCVerify)."""
+import gzip
+import json
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import golden_io as G
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "compat", "_build", "run_compat_app")
+LBS = ["none", "wm", "cm", "cta", "strict"]
+
+
+@pytest.fixture(scope="module")
+def dataset():
+    if not os.path.exists(EXE):
+        pytest.skip("compat/_build/run_compat_app not built (needs /root/reference at build time)")
+    d = tempfile.mkdtemp()
+    for f in ("p2p-31.e", "p2p-31.v"):
+        with gzip.open(os.path.join(G.GOLDEN, f + ".gz"), "rb") as i, open(os.path.join(d, f), "wb") as o:
+            shutil.copyfileobj(i, o)
+    yield d
+    shutil.rmtree(d, ignore_errors=True)
+
+
+def run(dataset, app, lb, **kw):
+    out = tempfile.mkdtemp()
+    cmd = [EXE, "--application", app, "--efile", os.path.join(dataset, "p2p-31.e"),
+           "--vfile", os.path.join(dataset, "p2p-31.v"), "--out_prefix", out, "--lb", lb]
+    for k, v in kw.items():
+        cmd += ["--" + k, str(v)]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    info = json.loads(p.stdout.strip().splitlines()[-1])
+    text = open(os.path.join(out, "result_frag_0")).read()
+    shutil.rmtree(out, ignore_errors=True)
+    lines = text.splitlines()
+    lines.sort(key=lambda l: int(l.split()[0]))       # `sort -k1n` of misc/app_tests.sh:7
+    return info, "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("lb", LBS)
+@pytest.mark.parametrize("directed", [0, 1])
+def test_sssp_exact(dataset, lb, directed):
+    _, text = run(dataset, "sssp", lb, sssp_source=6, directed=directed)
+    assert text == G.golden_lines("p2p-31-SSSP-directed" if directed else "p2p-31-SSSP")
+
+
+@pytest.mark.parametrize("lb", LBS)
+@pytest.mark.parametrize("directed", [0, 1])
+def test_bfs_exact(dataset, lb, directed):
+    info, text = run(dataset, "bfs", lb, bfs_source=6, directed=directed)
+    assert text == G.golden_lines("p2p-31-BFS-directed" if directed else "p2p-31-BFS")
+    assert info["supersteps"] > 2
+
+
+@pytest.mark.parametrize("lb", LBS)
+def test_pagerank_eps(dataset, lb):
+    _, text = run(dataset, "pagerank", lb, pr_mr=10, pr_d=0.85)
+    got = np.array([float(l.split()[1]) for l in text.splitlines()])
+    want = np.array([float(v) for _, v in G.golden_pairs("p2p-31-PR")])
+    assert G.eps_check(got, want, 1e-4)      # the reference GPU app accumulates in f32 (pagerank.h:27-35)
+
+
+@pytest.mark.parametrize("lb", LBS)
+def test_wcc_partition(dataset, lb):
+    _, text = run(dataset, "wcc", lb)
+    got = np.array([int(l.split()[1]) for l in text.splitlines()])
+    want = np.array([int(v) for _, v in G.golden_pairs("p2p-31-WCC")])
+    assert G.same_partition(got, want)
