@@ -219,6 +219,12 @@ typedef struct {
   gl_allreduce_fn allreduce; /* required when fnum > 1 */
   void* user;
   size_t landing_bytes;      /* per-peer landing buffer capacity (bytes)      */
+  size_t mirror_bytes;       /* per-peer capacity of the dense mirror-sync area
+                                (inner state -> outer copies, the reference's
+                                BatchShuffleMessageManager::SyncInnerVertices,
+                                grape/cuda/parallel/batch_shuffle_message_manager.h:142-220);
+                                0 = 8 bytes per inner vertex of the largest fragment
+                                is NOT assumed: pass it explicitly                */
 } gl_comm_desc;
 #define GL_IPC_HANDLE_BYTES 64
 int gl_comm_create(gl_comm_t** out, const gl_comm_desc* d);

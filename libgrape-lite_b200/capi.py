@@ -67,7 +67,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.
 
 class CommDesc(C.Structure):
     _fields_ = [("fid", C.c_uint32), ("fnum", C.c_uint32), ("allreduce", ALLREDUCE_FN), ("user", C.c_void_p),
-                ("landing_bytes", C.c_size_t)]
+                ("landing_bytes", C.c_size_t), ("mirror_bytes", C.c_size_t)]
 
 
 class EdgeOp(C.Structure):
@@ -266,7 +266,7 @@ class Comm:
     """Fragment-group communicator.  `allreduce(array, op)` reduces a numpy
     array in place across the group (op: 0 sum, 1 min, 2 max)."""
 
-    def __init__(self, fid, fnum, allreduce, landing_bytes):
+    def __init__(self, fid, fnum, allreduce, landing_bytes, mirror_bytes=0):
         self._py_allreduce = allreduce
 
         def _cb(user, ptr, n, is_double, op):
@@ -281,7 +281,7 @@ class Comm:
                 return 1
 
         self._cb = ALLREDUCE_FN(_cb)
-        d = CommDesc(fid, fnum, self._cb, None, landing_bytes)
+        d = CommDesc(fid, fnum, self._cb, None, landing_bytes, mirror_bytes)
         self.h = C.c_void_p()
         check(lib().gl_comm_create(C.byref(self.h), C.byref(d)))
         self.fid, self.fnum = fid, fnum

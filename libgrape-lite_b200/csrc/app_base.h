@@ -64,6 +64,7 @@ struct gl_app {
   virtual int Result(void* host_out, size_t bytes) = 0;
   virtual size_t ResultElemBytes() const = 0;
   virtual void FillStats(gl_query_stats*) {}   // apps that time supersteps on the device
+  virtual void AfterRound() {}                 // runs after every FinishARound (global round statistics)
   // record per-superstep stats (called by apps after fetch_ctrl)
   void note_step(uint64_t entries, uint32_t frontier, int mode) {
     rec.entries.push_back(entries);

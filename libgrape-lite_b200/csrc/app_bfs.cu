@@ -478,6 +478,7 @@ struct BfsApp : gl_app {
   uint32_t curr_depth = 0;
   // frontier statistics driving the push/pull switch (stepwise path)
   uint64_t n_f = 0, m_f = 0, visited_edges = 0;
+  uint64_t g_m_total = 0, g_vnum = 0;   // whole-graph totals (all fragments)
   uint32_t phase = 0;
   BfsFusedCtl* d_ctl = nullptr;
   BfsFusedCtl* h_ctl = nullptr;
@@ -495,7 +496,9 @@ struct BfsApp : gl_app {
   size_t ResultElemBytes() const override { return sizeof(int64_t); }
 
   uint32_t* level_bm(uint32_t d) { return lv + (size_t) d * words; }
-  const uint64_t* row_end() const { return fv.fnum > 1 ? fv.oe_split : fv.oe_rp + 1; }
+  // pull scans whole rows: with several fragments the frontier bits of the
+  // outer copies are refreshed from their owners first (mirror sync)
+  const uint64_t* row_end() const { return fv.oe_rp + 1; }
 
   // directed graphs: the pull step would need the incoming adjacency
   // (bfs.h:225-238); levels are identical with push only.
@@ -522,7 +525,18 @@ struct BfsApp : gl_app {
     GL_CUDA(cudaStreamSynchronize(eng.stream));
     used_lv = 0;
     // message = bare lid (bfs.h:50-51: sizeof(vid_t) per outer vertex)
-    return mm.Init(comm, fv, sizeof(ItemU32));
+    GL_TRY(mm.Init(comm, fv, sizeof(ItemU32)));
+    g_m_total = frag->oe.entries;
+    g_vnum = fv.ivnum;
+    if (fv.fnum > 1) {
+      GL_TRY(mm.BuildMirrorPlan(eng.stream, fv));
+      long long a = (long long) frag->oe.entries, b = (long long) fv.ivnum;
+      double c = 0;
+      GL_TRY(mm.PeerAllReduce(eng.stream, &a, &b, &c, 0));
+      g_m_total = (uint64_t) a;
+      g_vnum = (uint64_t) b;
+    }
+    return GL_OK;
   }
 
   int Init() override {
@@ -535,6 +549,8 @@ struct BfsApp : gl_app {
     used_lv = 0;
     n_f = m_f = visited_edges = 0;
     phase = 0;
+    rounds_noted = false;
+    pending_stats = false;
     return GL_OK;
   }
 
@@ -610,6 +626,12 @@ struct BfsApp : gl_app {
       GL_CUDA(cudaStreamSynchronize(eng.stream));
       n_f = 1;
       m_f = rp2[1] - rp2[0];
+    }
+    if (fv.fnum > 1) {
+      mm.stat_in[0] = (long long) n_f;
+      mm.stat_in[1] = (long long) m_f;
+      pending_stats = true;
+    } else {
       visited_edges = m_f;
     }
     used_lv = 1;
@@ -626,60 +648,88 @@ struct BfsApp : gl_app {
     uint32_t* cur = level_bm(curr_depth);
     uint32_t* nxt = level_bm(curr_depth + 1);
     GL_TRY(eng.reset_ctrl());
-    if (fv.fnum > 1) {
+    const bool multi = fv.fnum > 1;
+    if (multi) {
       // ParallelProcess (bfs.h:158-166): received vertices join the current level
       MsgView mv = mm.view();
       BfsApply ap{cur, vis, fv.oe_rp};
       GL_LAUNCH((k_unpack<ItemU32, BfsApply>), eng.sm_count * 4, kTB, s, mv, ap, eng.ctrl);
-      GL_TRY(eng.fetch_ctrl());
-      n_f += eng.h_ctrl->aux;
-      m_f += eng.h_ctrl->next_edges;
-      visited_edges += eng.h_ctrl->next_edges;
       GL_TRY(eng.reset_ctrl());
       GL_CUDA(cudaMemsetAsync(remote, 0, sizeof(uint32_t) * words, s));
     }
-    // direction choice; with several fragments every fragment decides on its
-    // own statistics like the reference does (bfs.h:171-180)
-    const uint64_t m_total = frag->oe.entries;
-    const uint64_t m_u = m_total > visited_edges ? m_total - visited_edges : 0;
+    // Direction choice on WHOLE-GRAPH statistics (identical on every fragment,
+    // because the pull step is collective: it starts with a mirror sync).
+    // n_f / m_f / visited_edges are global sums carried by the round vote.
+    const uint32_t prev_phase = phase;
+    const uint64_t m_u = g_m_total > visited_edges ? g_m_total - visited_edges : 0;
     if (!can_pull()) {
       phase = 0;
     } else if (phase == 0) {
       phase = (n_f > 0 && m_f > m_u / 14) ? 1 : 0;
     } else if (phase == 1) {
-      phase = (n_f >= (uint64_t) fv.ivnum / 24) ? 1 : (fv.fnum > 1 ? 0 : 2);
+      phase = (n_f >= g_vnum / 24) ? 1 : 2;
     }
     const bool use_pull = phase == 1;
     EdgeRange er{fv.oe_rp, fv.oe_col, nullptr};
     if (!use_pull) {
+      // leaving the pull phase: outer copies learn which vertices their owners
+      // visited meanwhile, so the push phase does not re-report them
+      if (multi && prev_phase == 1) GL_TRY(mm.SyncBitsToGhosts(s, vis));
       OpBfsPush op{vis, nxt, remote, fv.oe_rp, fv.ivnum};
       GL_TRY(run_frontier_scan(eng, cur, fv.ivnum, er, op));
+      if (multi) {
+        MsgView mv = mm.view();
+        GL_LAUNCH((k_pack_outer<ItemU32, BfsPayload>), eng.sm_count * 4, kTB, s, remote,
+                  fv.ivnum, fv.ovnum, fv.ovgid, mv, BfsPayload(), 0, nullptr);
+      }
     } else {
+      // pull: refresh the frontier bits of the outer copies from their owners
+      // (dense mirror sync over NVLink), then every unvisited inner vertex
+      // scans its whole row locally: no per-vertex messages in this phase
+      if (multi) GL_TRY(mm.SyncBitsToGhosts(s, cur));
       static thread_local int gp = 0;
       if (!gp) gp = persistent_grid(k_bfs_pull, eng.sm_count);
-      if (fv.ovnum) {
-        GL_LAUNCH(k_bfs_pull_outer, eng.sm_count * 8, kTB, s, fv.ovie_rp, fv.ovie_col,
-                  fv.ivnum, fv.ovnum, cur, vis, nxt, remote, eng.ctrl);
-      }
       GL_LAUNCH(k_bfs_pull, gp, kTB, s, pull_args(), cur, vis, nxt, eng.ctrl);
     }
-    if (fv.fnum > 1) {
-      MsgView mv = mm.view();
-      GL_LAUNCH((k_pack_outer<ItemU32, BfsPayload>), eng.sm_count * 4, kTB, s, remote,
-                fv.ivnum, fv.ovnum, fv.ovgid, mv, BfsPayload(), 0, nullptr);
+    step_pull = use_pull;
+    if (multi) {
+      // the round vote reads the device counters and mirrors them to the host:
+      // one host synchronisation per superstep (inside FinishARound)
+      mm.vote_ctrl = eng.ctrl;
+      mm.vote_h_ctrl = eng.h_ctrl;
+      pending_stats = true;
+    } else {
+      GL_TRY(eng.fetch_ctrl());
+      const ScanCtrl& c = *eng.h_ctrl;
+      note_step(c.scanned, (uint32_t) std::min<uint64_t>(n_f, 0xFFFFFFFFu), use_pull ? 1 : 0);
+      q_touched += c.touched;
+      if (c.next_count > 0) mm.ForceContinue();
+      n_f = c.next_count;
+      m_f = c.next_edges;
+      visited_edges += c.next_edges;
     }
-    GL_TRY(eng.fetch_ctrl());
-    const ScanCtrl& c = *eng.h_ctrl;
-    note_step(c.scanned, (uint32_t) std::min<uint64_t>(n_f, 0xFFFFFFFFu), use_pull ? 1 : 0);
-    q_touched += c.touched;
-    n_f = c.next_count;
-    m_f = c.next_edges;
-    visited_edges += c.next_edges;
-    if (c.next_count > 0) mm.ForceContinue();
     ++curr_depth;
     used_lv = curr_depth + 1;
     return GL_OK;
   }
+
+  // called by the worker after FinishARound
+  void AfterRound() override {
+    if (!pending_stats) return;
+    pending_stats = false;
+    if (rounds_noted) {
+      const ScanCtrl& c = *eng.h_ctrl;   // mirrored by the vote kernel
+      note_step(c.scanned, (uint32_t) std::min<uint64_t>(n_f, 0xFFFFFFFFu), step_pull ? 1 : 0);
+      q_touched += c.touched;
+    }
+    rounds_noted = true;
+    n_f = (uint64_t) mm.stat_out[0];
+    m_f = (uint64_t) mm.stat_out[1];
+    visited_edges += m_f;
+  }
+  bool pending_stats = false;
+  bool step_pull = false;
+  bool rounds_noted = false;   // PEval's vote carries no engine counters
 
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;

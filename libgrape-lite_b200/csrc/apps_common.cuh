@@ -1,6 +1,8 @@
 // apps_common.cuh — launch helpers and small kernels shared by the apps.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "app_base.h"
 
@@ -15,11 +17,27 @@ int persistent_grid(K kernel, int sm_count, int threads = kTB) {
   return per_sm * sm_count;
 }
 
-#define GL_LAUNCH(kernel, grid, block, stream, ...)          \
-  do {                                                       \
-    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);   \
-    GL_COUNT_LAUNCH();                                       \
-    GL_CUDA(cudaGetLastError());                             \
+// GL_TRACE=1 in the environment: synchronise after every launch and print its
+// wall time (debugging aid; never enabled in measurements)
+inline bool trace_on() {
+  static int on = -1;
+  if (on < 0) on = getenv("GL_TRACE") ? 1 : 0;
+  return on == 1;
+}
+#define GL_LAUNCH(kernel, grid, block, stream, ...)                                   \
+  do {                                                                                \
+    if (::gl::trace_on()) {                                                           \
+      cudaStreamSynchronize(stream);                                                  \
+      auto t0__ = std::chrono::steady_clock::now();                                   \
+      kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                          \
+      cudaStreamSynchronize(stream);                                                  \
+      fprintf(stderr, "[gl-trace] %-60s %8.1f us\n", #kernel,                         \
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0__).count()); \
+    } else {                                                                          \
+      kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                          \
+    }                                                                                 \
+    GL_COUNT_LAUNCH();                                                                \
+    GL_CUDA(cudaGetLastError());                                                      \
   } while (0)
 
 // Runs one frontier-driven edge scan (tile kernel + hub kernel) on `er`.
@@ -51,23 +69,33 @@ __global__ void __launch_bounds__(kTB)
 k_pack_outer(const uint32_t* __restrict__ remote, uint32_t ivnum, uint32_t ovnum,
              const uint32_t* __restrict__ ovgid, MsgView mv, Payload pay,
              int clear_bits, uint32_t* remote_rw) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t rounds = (ovnum + stride - 1) / stride;
-  uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint32_t r = 0; r < rounds; ++r, o += stride) {
-    bool pred = false;
-    uint32_t dst = 0;
-    Item it;
-    if (o < ovnum) {
-      uint32_t v = ivnum + o;
-      if (bit_test(remote, v)) {
-        uint32_t gid = ovgid[o];
+  // word-level scan of the outer part of the bitmap: a warp takes 32 words
+  // (1024 outer copies), skips all-zero groups, and for every non-zero word
+  // lets lane b test bit b, so msg_send runs warp-converged.
+  const uint32_t w_lo = ivnum >> 5;
+  const uint32_t w_hi = (ivnum + ovnum + 31) >> 5;          // exclusive
+  const uint32_t nwords = w_hi > w_lo ? w_hi - w_lo : 0;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t groups = (nwords + 31) >> 5;
+  for (uint32_t grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < groups; grp += warps) {
+    const uint32_t wi = w_lo + (grp << 5) + lane_id();
+    const uint32_t word = wi < w_hi ? remote[wi] : 0u;
+    uint32_t nzmask = __ballot_sync(0xffffffffu, word != 0);
+    while (nzmask) {
+      const uint32_t src = __ffs(nzmask) - 1;
+      nzmask &= nzmask - 1;
+      const uint32_t w = __shfl_sync(0xffffffffu, word, src);
+      const uint32_t v = ((w_lo + (grp << 5) + src) << 5) + lane_id();
+      bool pred = ((w >> lane_id()) & 1u) && v >= ivnum && v < ivnum + ovnum;
+      uint32_t dst = 0;
+      Item it;
+      if (pred) {
+        const uint32_t gid = ovgid[v - ivnum];
         dst = gid >> mv.fid_offset;
         it = pay(v, gid & mv.id_mask);
-        pred = true;
       }
+      msg_send<Item>(mv, pred, dst, it);
     }
-    msg_send<Item>(mv, pred, dst, it);
   }
   (void) clear_bits;
   (void) remote_rw;

@@ -1,5 +1,7 @@
 // comm.cu — landing-area allocation / CUDA-IPC mapping and the round protocol.
 #include "comm.h"
+#include "engine.cuh"
+#include "apps_common.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -33,8 +35,10 @@ __global__ void k_peer_allreduce(uint32_t fnum, uint32_t fid, PeerSlot* const* m
                                  const PeerSlot* local_slots, unsigned long long tag,
                                  long long i0, long long i1, double d0, int op,
                                  uint32_t* const* peer_count, uint32_t* send_count,
-                                 uint32_t* h_counts, PeerSlot* h_out) {
-  __shared__ long long s_i0[GL_MAX_FNUM], s_i1[GL_MAX_FNUM];
+                                 uint32_t* h_counts, PeerSlot* h_out, long long i2 = 0,
+                                 long long i3 = 0, const ScanCtrl* ctrl = nullptr,
+                                 ScanCtrl* h_ctrl = nullptr) {
+  __shared__ long long s_i0[GL_MAX_FNUM], s_i1[GL_MAX_FNUM], s_i2[GL_MAX_FNUM], s_i3[GL_MAX_FNUM];
   __shared__ double s_d0[GL_MAX_FNUM];
   __shared__ unsigned int s_total;
   const uint32_t p = threadIdx.x;
@@ -51,10 +55,20 @@ __global__ void k_peer_allreduce(uint32_t fnum, uint32_t fid, PeerSlot* const* m
   }
   __syncthreads();
   i1 += (long long) s_total;
+  if (ctrl) {
+    // vote taken from the engine's device counters
+    const unsigned long long nc = ctrl->next_count, rc = ctrl->remote_count, ne = ctrl->next_edges;
+    if (nc > 0) i0 = 1;
+    i2 = (long long) (nc + rc);
+    i3 = (long long) ne;
+    if (p == 0 && h_ctrl) *h_ctrl = *ctrl;
+  }
   if (p < fnum) {
     PeerSlot* dst = my_slot_at_peer[p];        // peer p's header, slot [me] (p == me: local)
     dst->i0 = i0;
     dst->i1 = i1;
+    dst->i2 = i2;
+    dst->i3 = i3;
     dst->d0 = d0;
     __threadfence_system();
     *(volatile unsigned long long*) &dst->tag = tag;
@@ -64,25 +78,212 @@ __global__ void k_peer_allreduce(uint32_t fnum, uint32_t fid, PeerSlot* const* m
     __threadfence_system();
     s_i0[p] = src->i0;
     s_i1[p] = src->i1;
+    s_i2[p] = src->i2;
+    s_i3[p] = src->i3;
     s_d0[p] = src->d0;
   }
   __syncthreads();
   if (p == 0) {
-    long long a = s_i0[0], b = s_i1[0];
+    long long a = s_i0[0], b = s_i1[0], e2 = s_i2[0], e3 = s_i3[0];
     double c = s_d0[0];
     for (uint32_t q = 1; q < fnum; ++q) {
+      e2 += s_i2[q];
+      e3 += s_i3[q];
       if (op == 0) { a += s_i0[q]; b += s_i1[q]; c += s_d0[q]; }
       else if (op == 1) { a = a < s_i0[q] ? a : s_i0[q]; b = b < s_i1[q] ? b : s_i1[q]; c = c < s_d0[q] ? c : s_d0[q]; }
       else { a = a > s_i0[q] ? a : s_i0[q]; b = b > s_i1[q] ? b : s_i1[q]; c = c > s_d0[q] ? c : s_d0[q]; }
     }
     h_out->i0 = a;
     h_out->i1 = b;
+    h_out->i2 = e2;
+    h_out->i3 = e3;
     h_out->d0 = c;
     h_out->tag = tag;
   }
   (void) fid;
 }
+
+// ---- dense mirror sync ------------------------------------------------------
+// holder side of the plan: tell every owner which of its inner lids I hold
+__global__ void k_mirror_request(const uint32_t* __restrict__ ovgid, uint32_t ivnum, uint32_t ovnum,
+                                 const uint32_t* __restrict__ ghost_range, uint32_t fnum,
+                                 uint32_t id_mask, char* const* msend) {
+  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < ovnum; o += gridDim.x * blockDim.x) {
+    const uint32_t lid = ivnum + o;
+    uint32_t f = 0;
+    while (f + 1 < fnum && lid >= ghost_range[f + 1]) ++f;
+    ((uint32_t*) msend[f])[lid - ghost_range[f]] = ovgid[o] & id_mask;
+  }
+}
+__global__ void k_mirror_counts(const uint32_t* __restrict__ ghost_range, uint32_t fnum, uint32_t fid,
+                                uint32_t* const* peer_count) {
+  uint32_t f = threadIdx.x;
+  if (f < fnum && f != fid) *peer_count[f] = ghost_range[f + 1] - ghost_range[f];
+  __threadfence_system();
+}
+// owner side: pack the bits of my mirrored vertices, 32 per word, per holder
+__global__ void k_mirror_pack_bits(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ lids,
+                                   const uint64_t* __restrict__ off, char* const* msend) {
+  const uint32_t g = blockIdx.y;
+  const uint64_t b = off[g], n = off[g + 1] - b;
+  uint32_t* out = (uint32_t*) msend[g];
+  const uint64_t npad = (n + 31) & ~31ull;
+  for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < npad; k += (uint64_t) gridDim.x * blockDim.x) {
+    bool bit = false;
+    if (k < n) bit = bit_test(bitmap, lids[b + k]);
+    uint32_t w = __ballot_sync(0xffffffffu, bit);
+    if ((threadIdx.x & 31) == 0) out[k >> 5] = w;
+  }
+}
+// holder side: OR the received words into the ghost positions of my bitmap
+// (one thread per 32 outer copies; the ghost range of an owner is contiguous
+// but not word aligned, hence the two-part shifted OR)
+__global__ void k_mirror_unpack_bits(uint32_t* bitmap, const uint32_t* __restrict__ ghost_range,
+                                     const char* const* mrecv) {
+  const uint32_t f = blockIdx.y;
+  const uint32_t base = ghost_range[f], n = ghost_range[f + 1] - base;
+  const uint32_t nw = (n + 31) >> 5;
+  const uint32_t* in = (const uint32_t*) mrecv[f];
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nw; j += gridDim.x * blockDim.x) {
+    const uint32_t w = __ldcg(in + j);   // written by the peer: bypass L1
+    if (!w) continue;
+    const uint32_t pos = base + (j << 5), sh = pos & 31;
+    atomicOr(bitmap + (pos >> 5), w << sh);
+    if (sh) atomicOr(bitmap + (pos >> 5) + 1, w >> (32 - sh));
+  }
+}
+template <typename T>
+__global__ void k_mirror_pack_vals(const T* __restrict__ values, const uint32_t* __restrict__ lids,
+                                   const uint64_t* __restrict__ off, char* const* msend) {
+  const uint32_t g = blockIdx.y;
+  const uint64_t b = off[g], n = off[g + 1] - b;
+  T* out = (T*) msend[g];
+  for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t) gridDim.x * blockDim.x)
+    out[k] = values[lids[b + k]];
+}
+template <typename T>
+__global__ void k_mirror_unpack_vals(T* values, const uint32_t* __restrict__ ghost_range,
+                                     const char* const* mrecv) {
+  const uint32_t f = blockIdx.y;
+  const uint32_t base = ghost_range[f], n = ghost_range[f + 1] - base;
+  const T* in = (const T*) mrecv[f];
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    values[base + k] = in[k];
+}
 }  // namespace
+
+int MessageManager::PeerBarrier(cudaStream_t s) {
+  long long a = 0, b = 0;
+  double c = 0;
+  return PeerAllReduce(s, &a, &b, &c, 0);
+}
+
+int MessageManager::PeerBarrierAsync(cudaStream_t s) {
+  const unsigned long long tag = ++comm->seq_base;
+  const int par = (int) (tag & 1);
+  const PeerSlot* local = (const PeerSlot*) (comm->local_base + GL_COMM_SLOT_OFF) + (size_t) par * GL_MAX_FNUM;
+  if (!d_scratch_result) GL_CUDA(cudaMalloc(&d_scratch_result, sizeof(PeerSlot)));
+  GL_LAUNCH(k_peer_allreduce, 1, GL_MAX_FNUM, s, fnum, fid, d_peer_slot[par], local, tag, 0ll, 0ll, 0.0, 0,
+            nullptr, nullptr, nullptr, d_scratch_result, 0ll, 0ll, nullptr, nullptr);
+  return GL_OK;
+}
+
+int MessageManager::BuildMirrorPlan(cudaStream_t s, const gl_frag_view& fv) {
+  plan_built = true;
+  plan_ivnum = fv.ivnum;
+  if (fnum == 1) return GL_OK;
+  if (comm->mirror_bytes == 0) {
+    set_error("communicator was created without a mirror-sync area (mirror_bytes = 0)");
+    return GL_ERR_COMM;
+  }
+  // tables of mirror slots
+  for (int par = 0; par < 2; ++par) {
+    std::vector<char*> snd(fnum);
+    std::vector<const char*> rcv(fnum);
+    for (uint32_t p = 0; p < fnum; ++p) {
+      snd[p] = comm->peer_base[p] + comm->mirror_off(par, fid);
+      rcv[p] = comm->local_base + comm->mirror_off(par, p);
+    }
+    GL_CUDA(cudaMalloc(&d_msend[par], sizeof(char*) * fnum));
+    GL_CUDA(cudaMalloc(&d_mrecv[par], sizeof(char*) * fnum));
+    GL_CUDA(cudaMemcpy(d_msend[par], snd.data(), sizeof(char*) * fnum, cudaMemcpyHostToDevice));
+    GL_CUDA(cudaMemcpy(d_mrecv[par], rcv.data(), sizeof(char*) * fnum, cudaMemcpyHostToDevice));
+  }
+  ghost_range.resize(fnum + 1);
+  GL_CUDA(cudaMemcpy(ghost_range.data(), fv.outer_range, sizeof(uint32_t) * (fnum + 1), cudaMemcpyDeviceToHost));
+  d_ghost_range = const_cast<uint32_t*>(fv.outer_range);
+  for (uint32_t f = 0; f < fnum; ++f) {
+    if ((size_t) (ghost_range[f + 1] - ghost_range[f]) * 8 > comm->mirror_bytes) {
+      set_error("mirror-sync area too small: %u outer copies of fragment %u", ghost_range[f + 1] - ghost_range[f], f);
+      return GL_ERR_COMM;
+    }
+  }
+  GL_TRY(PeerBarrier(s));  // every rank's area is mapped and idle
+  // 1. requests: my ghosts' owner-lids, in ghost order, into the owner's slot (parity 0)
+  if (fv.ovnum) {
+    k_mirror_request<<<148 * 4, 256, 0, s>>>(fv.ovgid, fv.ivnum, fv.ovnum, d_ghost_range, fnum, id_mask, d_msend[0]);
+    GL_COUNT_LAUNCH();
+  }
+  k_mirror_counts<<<1, GL_MAX_FNUM, 0, s>>>(d_ghost_range, fnum, fid, d_peer_count[0]);
+  GL_COUNT_LAUNCH();
+  GL_CUDA(cudaGetLastError());
+  GL_TRY(PeerBarrier(s));
+  // 2. owner: read how many lids every holder sent, copy the lists out
+  std::vector<uint32_t> cnt(GL_MAX_FNUM);
+  GL_CUDA(cudaMemcpy(cnt.data(), comm->local_base, sizeof(uint32_t) * GL_MAX_FNUM, cudaMemcpyDeviceToHost));
+  mirror_off.assign(fnum + 1, 0);
+  for (uint32_t g = 0; g < fnum; ++g) mirror_off[g + 1] = mirror_off[g] + (g == fid ? 0 : cnt[g]);
+  mirror_total = mirror_off[fnum];
+  GL_CUDA(cudaMalloc(&d_mirror_lids, sizeof(uint32_t) * std::max<uint64_t>(mirror_total, 1)));
+  GL_CUDA(cudaMalloc(&d_mirror_off, sizeof(uint64_t) * (fnum + 1)));
+  GL_CUDA(cudaMemcpy(d_mirror_off, mirror_off.data(), sizeof(uint64_t) * (fnum + 1), cudaMemcpyHostToDevice));
+  for (uint32_t g = 0; g < fnum; ++g) {
+    if (g == fid || cnt[g] == 0) continue;
+    GL_CUDA(cudaMemcpyAsync(d_mirror_lids + mirror_off[g], comm->local_base + comm->mirror_off(0, g),
+                            sizeof(uint32_t) * cnt[g], cudaMemcpyDeviceToDevice, s));
+  }
+  // the message-count cells were borrowed: clear them for the first round
+  GL_CUDA(cudaMemsetAsync(comm->local_base, 0, sizeof(uint32_t) * 2 * GL_MAX_FNUM, s));
+  GL_TRY(PeerBarrier(s));
+  mirror_seq = 0;
+  return GL_OK;
+}
+
+int MessageManager::SyncBitsToGhosts(cudaStream_t s, uint32_t* bitmap) {
+  if (fnum == 1) return GL_OK;
+  const int par = (int) (++mirror_seq & 1);
+  if (mirror_total) {
+    dim3 grid(148 * 8, fnum);
+    GL_LAUNCH(k_mirror_pack_bits, grid, 256, s, bitmap, d_mirror_lids, d_mirror_off, d_msend[par]);
+  }
+  GL_TRY(PeerBarrierAsync(s));
+  if (ghost_range[fnum] > ghost_range[0]) {
+    dim3 grid(148 * 2, fnum);
+    GL_LAUNCH(k_mirror_unpack_bits, grid, 256, s, bitmap, d_ghost_range, d_mrecv[par]);
+  }
+  return GL_OK;
+}
+
+int MessageManager::SyncValuesToGhosts(cudaStream_t s, void* values, int elem_bytes) {
+  if (fnum == 1) return GL_OK;
+  const int par = (int) (++mirror_seq & 1);
+  dim3 grid(148 * 8, fnum);
+  if (mirror_total) {
+    if (elem_bytes == 4) k_mirror_pack_vals<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*) values, d_mirror_lids, d_mirror_off, d_msend[par]);
+    else k_mirror_pack_vals<uint64_t><<<grid, 256, 0, s>>>((const uint64_t*) values, d_mirror_lids, d_mirror_off, d_msend[par]);
+    GL_COUNT_LAUNCH();
+    GL_CUDA(cudaGetLastError());
+  }
+  GL_TRY(PeerBarrierAsync(s));
+  if (ghost_range[fnum] > ghost_range[0]) {
+    if (elem_bytes == 4) k_mirror_unpack_vals<uint32_t><<<grid, 256, 0, s>>>((uint32_t*) values, d_ghost_range, d_mrecv[par]);
+    else k_mirror_unpack_vals<uint64_t><<<grid, 256, 0, s>>>((uint64_t*) values, d_ghost_range, d_mrecv[par]);
+    GL_COUNT_LAUNCH();
+    GL_CUDA(cudaGetLastError());
+  }
+  return GL_OK;
+}
+
 
 int MessageManager::PeerAllReduce(cudaStream_t s, long long* i0, long long* i1, double* d0, int op) {
   const unsigned long long tag = ++comm->seq_base;
@@ -154,6 +355,18 @@ void MessageManager::Destroy() {
     d_recv_slot[par] = nullptr;
     d_peer_count[par] = nullptr;
   }
+  for (int par = 0; par < 2; ++par) {
+    if (d_msend[par]) cudaFree(d_msend[par]);
+    if (d_mrecv[par]) cudaFree((void*) d_mrecv[par]);
+    d_msend[par] = nullptr;
+    d_mrecv[par] = nullptr;
+  }
+  if (d_mirror_lids) cudaFree(d_mirror_lids);
+  if (d_mirror_off) cudaFree(d_mirror_off);
+  if (d_scratch_result) cudaFree(d_scratch_result);
+  d_scratch_result = nullptr;
+  d_mirror_lids = nullptr;
+  d_mirror_off = nullptr;
   if (d_send_count) cudaFree(d_send_count);
   if (h_send_count) cudaFreeHost(h_send_count);
   if (h_result) cudaFreeHost(h_result);
@@ -198,12 +411,18 @@ int MessageManager::FinishARound(cudaStream_t s) {
       const int bp = (int) (tag & 1);
       const PeerSlot* local = (const PeerSlot*) (comm->local_base + GL_COMM_SLOT_OFF) + (size_t) bp * GL_MAX_FNUM;
       k_peer_allreduce<<<1, GL_MAX_FNUM, 0, s>>>(fnum, fid, d_peer_slot[bp], local, tag, (long long) vote[0], 0ll,
-                                                 0.0, 0, d_peer_count[par], d_send_count, h_send_count, h_result);
+                                                 0.0, 0, d_peer_count[par], d_send_count, h_send_count, h_result,
+                                                 stat_in[0], stat_in[1], vote_ctrl, vote_h_ctrl);
+      vote_ctrl = nullptr;
+      vote_h_ctrl = nullptr;
       GL_COUNT_LAUNCH();
       GL_CUDA(cudaGetLastError());
       GL_CUDA(cudaStreamSynchronize(s));
       vote[0] = h_result->i0;
       vote[1] = h_result->i1;
+      stat_out[0] = h_result->i2;
+      stat_out[1] = h_result->i3;
+      stat_in[0] = stat_in[1] = 0;
     } else {
       k_publish_counts<<<1, GL_MAX_FNUM, 0, s>>>(fnum, fid, d_peer_count[par], d_send_count, h_send_count);
       GL_COUNT_LAUNCH();
@@ -282,6 +501,7 @@ int gl_comm_create(gl_comm_t** out, const gl_comm_desc* d) {
   c->allreduce = d->allreduce;
   c->user = d->user;
   c->landing_bytes = (d->landing_bytes + 255) & ~(size_t) 255;
+  c->mirror_bytes = (d->mirror_bytes + 255) & ~(size_t) 255;
   cudaError_t e = cudaMalloc(&c->local_base, c->total_bytes());
   if (e != cudaSuccess) {
     set_error("landing area (%zu bytes): %s", c->total_bytes(), cudaGetErrorString(e));

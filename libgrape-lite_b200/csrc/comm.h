@@ -21,12 +21,12 @@
 constexpr uint32_t GL_MAX_FNUM = 64;
 // Header of a landing area: item counts + the peer-barrier slots.
 //   [0, 512)      uint32 counts[2][GL_MAX_FNUM]
-//   [1024, 5120)  PeerSlot slots[2][GL_MAX_FNUM]   (32 B each)
+//   [1024, 7168)  PeerSlot slots[2][GL_MAX_FNUM]   (48 B each)
 constexpr size_t GL_COMM_HEADER = 8192;
 constexpr size_t GL_COMM_SLOT_OFF = 1024;
-struct PeerSlot {            // one rank's contribution to a collective
+struct PeerSlot {            // one rank's contribution to a collective (48 B)
   unsigned long long tag;    // sequence number, written last (release)
-  long long i0, i1;
+  long long i0, i1, i2, i3;
   double d0;
 };
 
@@ -34,17 +34,25 @@ struct gl_comm {
   uint32_t fid = 0, fnum = 1;
   gl_allreduce_fn allreduce = nullptr;
   void* user = nullptr;
-  size_t landing_bytes = 0;  // per (parity, src) slot
+  size_t landing_bytes = 0;  // per (parity, src) message slot
+  size_t mirror_bytes = 0;   // per (parity, src) mirror-sync slot
   char* local_base = nullptr;
   std::vector<char*> peer_base;  // [fnum]; peer_base[fid] == local_base
   bool opened = false;
   unsigned long long seq_base = 0;  // last collective sequence number used on this communicator
   size_t total_bytes() const {
-    return GL_COMM_HEADER + 2 * (size_t) fnum * landing_bytes;
+    return GL_COMM_HEADER + 2 * (size_t) fnum * (landing_bytes + mirror_bytes);
+  }
+  // byte offset of the mirror slot (parity, src) inside a landing area
+  size_t mirror_off(int parity, uint32_t src) const {
+    return GL_COMM_HEADER + 2 * (size_t) fnum * landing_bytes +
+           ((size_t) parity * fnum + src) * mirror_bytes;
   }
 };
 
 namespace gl {
+
+struct ScanCtrl;  // engine.cuh
 
 // Device-side view handed to producer / consumer kernels.
 struct MsgView {
@@ -95,6 +103,38 @@ struct MessageManager {
   // fid order => bit-identical on all ranks.  Also a barrier: it is issued
   // after the round's peer stores on the same stream.
   int PeerAllReduce(cudaStream_t s, long long* i0, long long* i1, double* d0, int op);
+  int PeerBarrier(cudaStream_t s);
+  // barrier only: enqueued on the stream, no host synchronisation
+  int PeerBarrierAsync(cudaStream_t s);
+  // When set, FinishARound's kernel takes the vote straight from the engine's
+  // device counters (force_continue |= next_count > 0, statistics = next_count
+  // + remote_count, next_edges) and mirrors the control block to `vote_h_ctrl`,
+  // so a round closes with ONE host synchronisation.
+  const ScanCtrl* vote_ctrl = nullptr;
+  ScanCtrl* vote_h_ctrl = nullptr;
+  PeerSlot* d_scratch_result = nullptr;
+  // ---- dense mirror sync (owner's inner state -> the outer copies held by
+  // other fragments); replaces BatchShuffleMessageManager::SyncInnerVertices.
+  // BuildMirrorPlan is collective and must run once (Setup); afterwards every
+  // Sync* call is collective too.
+  int BuildMirrorPlan(cudaStream_t s, const gl_frag_view& fv);
+  bool has_mirror_plan() const { return d_mirror_lids != nullptr || mirror_total == 0 && plan_built; }
+  int SyncBitsToGhosts(cudaStream_t s, uint32_t* bitmap);   // ghost bits |= owner bits
+  int SyncValuesToGhosts(cudaStream_t s, void* values, int elem_bytes);  // values[ghost] = owner value
+  bool plan_built = false;
+  uint32_t plan_ivnum = 0;
+  uint32_t* d_mirror_lids = nullptr;        // my inner lids mirrored elsewhere, grouped by holder
+  uint64_t* d_mirror_off = nullptr;         // device [fnum+1]
+  std::vector<uint64_t> mirror_off;         // host  [fnum+1]
+  uint64_t mirror_total = 0;
+  uint32_t* d_ghost_range = nullptr;        // device [fnum+1]: outer lids owned by each fid (outer_range)
+  std::vector<uint32_t> ghost_range;
+  char** d_msend[2] = {nullptr, nullptr};        // [parity][fnum] mirror slot (parity, me) at peer
+  const char** d_mrecv[2] = {nullptr, nullptr};  // [parity][fnum] my mirror slot (parity, src)
+  unsigned long long mirror_seq = 0;
+  // extra statistics carried by the round vote (summed over fragments)
+  long long stat_in[2] = {0, 0};
+  long long stat_out[2] = {0, 0};
   bool use_peer_barrier = true;
   cudaStream_t stream_for_collectives = nullptr;
   unsigned long long seq = 0;

@@ -130,12 +130,14 @@ int gl_app_query(gl_app_t* a, gl_query_stats* stats) {
   GL_TRY(a->mm.StartARound(s));
   GL_TRY(a->PEval());
   GL_TRY(a->mm.FinishARound(s));
+  a->AfterRound();
   GL_CUDA(cudaEventRecord(a->rec.next(), s));
   a->rounds = 1;
   while (!a->mm.ToTerminate()) {
     GL_TRY(a->mm.StartARound(s));
     GL_TRY(a->IncEval());
     GL_TRY(a->mm.FinishARound(s));
+    a->AfterRound();
     GL_CUDA(cudaEventRecord(a->rec.next(), s));
     ++a->rounds;
     if (a->rounds > 1000000) {

@@ -32,7 +32,8 @@ def make_comm(rank, world, ivnum, item_bytes=16, group=None):
         iv = iv.cuda()
     dist.all_reduce(iv, op=dist.ReduceOp.MAX, group=group)
     landing = item_bytes * (int(iv.item()) + 1024)
-    comm = capi.Comm(rank, world, allreduce, landing_bytes=landing)
+    # dense mirror sync: up to 8 bytes (f64 / int64 state) per inner vertex of the owner
+    comm = capi.Comm(rank, world, allreduce, landing_bytes=landing, mirror_bytes=8 * (int(iv.item()) + 1024))
     handles = [None] * world
     dist.all_gather_object(handles, comm.export(), group=group)
     comm.open(handles)
