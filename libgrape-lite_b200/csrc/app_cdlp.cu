@@ -112,10 +112,6 @@ struct CdlpApp : gl_app {
   size_t ResultElemBytes() const override { return sizeof(int64_t); }
 
   int Setup() override {
-    if (fv.fnum > 1) {
-      set_error("CDLP on fnum > 1 needs the mirror sync of inner labels (next row); run it on one fragment");
-      return GL_ERR_STATE;
-    }
     tvnum = fv.ivnum + fv.ovnum;
     const uint64_t m = frag->oe.entries;
     GL_CUDA(cudaMalloc(&label, sizeof(uint32_t) * std::max<uint32_t>(tvnum, 1)));
@@ -126,7 +122,11 @@ struct CdlpApp : gl_app {
     GL_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, sort_bytes, scratch, sorted, (int64_t) m,
                                                (int64_t) fv.ivnum, fv.oe_rp, fv.oe_rp + 1, eng.stream));
     GL_CUDA(cudaMalloc(&sort_tmp, std::max<size_t>(sort_bytes, 16)));
-    return mm.Init(comm, fv, sizeof(ItemU32U32));
+    GL_TRY(mm.Init(comm, fv, sizeof(ItemU32U32)));
+    // outer copies read their owner's label every round (dense mirror sync;
+    // the reference ships changed labels with SendMsgThroughOEdges, cdlp.h:69-70)
+    if (fv.fnum > 1) GL_TRY(mm.BuildMirrorPlan(eng.stream, fv));
+    return GL_OK;
   }
 
   int Init() override {
@@ -137,6 +137,7 @@ struct CdlpApp : gl_app {
   int Propagate() {
     cudaStream_t s = eng.stream;
     const uint64_t m = frag->oe.entries;
+    if (fv.fnum > 1 && step > 1) GL_TRY(mm.SyncValuesToGhosts(s, label, 4));
     if (m) {
       GL_LAUNCH(k_cdlp_gather, eng.sm_count * 8, 256, s, fv.oe_col, m, label, scratch);
       GL_CUDA(cub::DeviceSegmentedSort::SortKeys(sort_tmp, sort_bytes, scratch, sorted, (int64_t) m,

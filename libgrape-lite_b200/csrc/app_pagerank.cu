@@ -154,13 +154,11 @@ struct PageRankApp : gl_app {
     GL_CUDA(cudaMalloc(&all_inner, sizeof(uint32_t) * words));
     GL_LAUNCH(k_ones, (unsigned) ((words + 255) / 256), 256, eng.stream, all_inner, fv.ivnum, (uint32_t) words);
     if (cfg.pr_pull) {
-      if (fv.fnum > 1) {
-        set_error("pr_pull needs the dense mirror sync (not available for fnum > 1); use push");
-        return GL_ERR_ARG;
-      }
-      GL_CUDA(cudaMalloc(&contrib, sizeof(double) * std::max<uint32_t>(fv.ivnum, 1)));
+      GL_CUDA(cudaMalloc(&contrib, sizeof(double) * std::max<uint32_t>(tvnum, 1)));
     }
-    return mm.Init(comm, fv, sizeof(ItemU32F64));
+    GL_TRY(mm.Init(comm, fv, sizeof(ItemU32F64)));
+    if (cfg.pr_pull && fv.fnum > 1) GL_TRY(mm.BuildMirrorPlan(eng.stream, fv));
+    return GL_OK;
   }
 
   int Init() override {
@@ -199,6 +197,10 @@ struct PageRankApp : gl_app {
       if (!gp) gp = persistent_grid(k_pr_pull, eng.sm_count);
       if (fv.ivnum) {
         GL_LAUNCH(k_pr_contrib, (fv.ivnum + 255) / 256, 256, s, rank, fv.oe_rp, fv.ivnum, contrib);
+      }
+      // outer copies take their owner's contribution (dense mirror sync)
+      if (fv.fnum > 1) GL_TRY(mm.SyncValuesToGhosts(s, contrib, 8));
+      if (fv.ivnum) {
         GL_LAUNCH(k_pr_pull, gp, kTB, s, fv.oe_rp, fv.oe_col, contrib, next, fv.ivnum, base, cfg.pr_delta, eng.ctrl);
       }
     } else {

@@ -30,7 +30,7 @@ def main():
         dist.all_gather_object(out, arr)
         return np.concatenate(out)
 
-    for wmode, apps in ((0, ["bfs", "bfs_push", "wcc", "pagerank"]), (1, ["sssp"])):
+    for wmode, apps in ((0, ["bfs", "bfs_push", "wcc", "pagerank", "pagerank_pull", "cdlp"]), (1, ["sssp"])):
         n = 1 << scale
         frag = pkg.Fragment.rmat(scale, 16, seed=17, weight_mode=wmode, fid=rank, fnum=world)
         comm = gdist.make_comm(rank, world, frag.ivnum)
@@ -52,8 +52,11 @@ def main():
                 cfg = dict(source_oid=source, direction_opt=0 if name == "bfs_push" else 1)
             elif name == "sssp":
                 cfg = dict(source_oid=source)
-            elif name == "pagerank":
-                cfg = dict(pr_delta=0.85, max_round=10)
+            elif name.startswith("pagerank"):
+                kind = "pagerank"
+                cfg = dict(pr_delta=0.85, max_round=10, pr_pull=1 if name.endswith("pull") else 0)
+            elif name == "cdlp":
+                cfg = dict(max_round=5)
             app = pkg.App(kind, frag, comm, **cfg)
             st = app.query()
             got = gather(app.result())
@@ -64,6 +67,8 @@ def main():
                     ok = np.array_equal(got, g.sssp(source)[0])
                 elif kind == "wcc":
                     ok = np.array_equal(got, g.wcc()[0].astype(np.int64))
+                elif kind == "cdlp":
+                    ok = np.array_equal(got, g.cdlp(5))
                 else:
                     want = g.pagerank(0.85, 10, 1)
                     ok = bool(np.max(np.abs(got - want) / want) < 1e-6)
