@@ -152,6 +152,8 @@ def run_gpu(args):
         cfg["fuse_supersteps"] = 0 if args.no_fuse else 1
     if args.app in ("pagerank", "cdlp"):
         cfg["max_round"] = 10
+    if args.app == "pagerank" and args.pr_pull:
+        cfg["pr_pull"] = 1
     app = pkg.App(args.app, frag, comm, **cfg)
 
     pinned = pkg.PinnedBuffer(8 * max(frag.ivnum, 1))
@@ -354,6 +356,7 @@ def main():
     ap.add_argument("--push-only", action="store_true")
     ap.add_argument("--cpu-scale", type=int, default=22, help="largest scale the CPU arm runs (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pr-pull", action="store_true", help="PageRank: deterministic pull step instead of atomicAdd push")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per superstep (profiling) instead of the fused query kernel")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -2,7 +2,7 @@
  *
  * The reference (alibaba/libgrape-lite @ e7c4465) exposes NO C ABI: its GPU
  * path is header-only C++ compiled into each app.  This header is the thin
- * boundary the reference's C++ host would bind instead of grape/cuda/**:
+ * boundary the reference's C++ host would bind instead of grape/cuda/ **:
  * every entry point cites the reference interface it replaces
  * (paths relative to the reference root).  Plain pointers and sizes only.
  *

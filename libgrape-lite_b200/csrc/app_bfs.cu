@@ -61,6 +61,13 @@ struct OpBfsPush {
   }
 };
 
+__global__ void k_bfs_nz(const uint64_t* rp, uint32_t n, uint32_t* nz) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool has = i < n && rp[i + 1] > rp[i];
+  uint32_t w = __ballot_sync(0xffffffffu, has);
+  if ((threadIdx.x & 31) == 0 && i < n) nz[i >> 5] = w;
+}
+
 __global__ void k_bfs_seed(uint32_t src, uint32_t* lv0, uint32_t* vis) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     lv0[src >> 5] |= 1u << (src & 31);
@@ -453,12 +460,14 @@ struct BfsApply {
 };
 
 // depth[v] = first level whose bitmap holds v (coalesced: a warp shares words)
+// (perm != null: the bitmaps are indexed by the hub-first rank of the vertex)
 __global__ void k_depth_from_levels(const uint32_t* lv, uint32_t words,
-                                    uint32_t nlevels, uint32_t n, int64_t* out) {
+                                    uint32_t nlevels, uint32_t n, const uint32_t* perm, int64_t* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int64_t d = INT64_MAX;
-  const uint32_t w = i >> 5, m = 1u << (i & 31);
+  const uint32_t pi = perm ? perm[i] : i;
+  const uint32_t w = pi >> 5, m = 1u << (pi & 31);
   for (uint32_t l = 0; l < nlevels; ++l) {
     if (lv[(size_t) l * words + w] & m) {
       d = (int64_t) l;
@@ -471,6 +480,15 @@ __global__ void k_depth_from_levels(const uint32_t* lv, uint32_t words,
 struct BfsApp : gl_app {
   uint32_t *lv = nullptr, *vis = nullptr, *remote = nullptr, *hub_nbr = nullptr;
   int64_t* out64 = nullptr;
+  // the adjacency BFS runs on: the fragment's own CSR, or (single fragment) a
+  // hub-first relabelled shadow copy — see hub_order.cu
+  const uint64_t* g_rp = nullptr;
+  const uint32_t* g_col = nullptr;
+  const uint32_t* g_nz = nullptr;
+  uint32_t *perm = nullptr, *order = nullptr, *nz_p = nullptr, *col_p = nullptr;
+  uint64_t* rp_p = nullptr;
+  uint32_t src_ = 0;
+  int has_src_ = 0;
   size_t words = 0;
   uint32_t tvnum = 0;
   uint32_t max_lv = 0;
@@ -492,13 +510,18 @@ struct BfsApp : gl_app {
     cudaFree(remote);
     cudaFree(hub_nbr);
     cudaFree(out64);
+    cudaFree(perm);
+    cudaFree(order);
+    cudaFree(nz_p);
+    cudaFree(col_p);
+    cudaFree(rp_p);
   }
   size_t ResultElemBytes() const override { return sizeof(int64_t); }
 
   uint32_t* level_bm(uint32_t d) { return lv + (size_t) d * words; }
   // pull scans whole rows: with several fragments the frontier bits of the
   // outer copies are refreshed from their owners first (mirror sync)
-  const uint64_t* row_end() const { return fv.oe_rp + 1; }
+  const uint64_t* row_end() const { return g_rp + 1; }
 
   // directed graphs: the pull step would need the incoming adjacency
   // (bfs.h:225-238); levels are identical with push only.
@@ -520,8 +543,25 @@ struct BfsApp : gl_app {
     GL_CUDA(cudaMalloc(&d_ctl, sizeof(BfsFusedCtl)));
     GL_CUDA(cudaMallocHost(&h_ctl, sizeof(BfsFusedCtl)));
     memset(h_ctl, 0, sizeof(BfsFusedCtl));
+    g_rp = fv.oe_rp;
+    g_col = fv.oe_col;
+    g_nz = frag->nonzero_deg;
+    // hub-first shadow graph (one fragment, undirected, large enough to matter)
+    if (fv.fnum == 1 && can_pull() && fv.ivnum >= (1u << 16) && cfg.reserved[1] == 0) {
+      GL_TRY(build_hub_order(eng.stream, fv.oe_rp, fv.ivnum, &perm, &order));
+      GL_TRY(build_permuted_csr(eng.stream, fv.oe_rp, fv.oe_col, frag->oe.entries, fv.ivnum, order, perm, &rp_p, &col_p));
+      GL_CUDA(cudaMalloc(&nz_p, sizeof(uint32_t) * words));
+      GL_CUDA(cudaMemsetAsync(nz_p, 0, sizeof(uint32_t) * words, eng.stream));
+      GL_LAUNCH(k_bfs_nz, (fv.ivnum + 255) / 256, 256, eng.stream, rp_p, fv.ivnum, nz_p);
+      g_rp = rp_p;
+      g_col = col_p;
+      g_nz = nz_p;
+    }
     if (fv.ivnum && can_pull())
-      GL_LAUNCH(k_bfs_hub_nbr, eng.sm_count * 8, 256, eng.stream, fv.oe_rp, row_end(), fv.oe_col, fv.ivnum, hub_nbr);
+      GL_LAUNCH(k_bfs_hub_nbr, eng.sm_count * 8, 256, eng.stream, g_rp, row_end(), g_col, fv.ivnum, hub_nbr);
+    // the source is fixed per app (AppConfig): resolve it once
+    has_src_ = gl_frag_oid2lid(frag, cfg.source_oid, &src_) == GL_OK ? 1 : 0;
+    if (has_src_ && perm) GL_CUDA(cudaMemcpy(&src_, perm + src_, 4, cudaMemcpyDeviceToHost));
     GL_CUDA(cudaStreamSynchronize(eng.stream));
     used_lv = 0;
     // message = bare lid (bfs.h:50-51: sizeof(vid_t) per outer vertex)
@@ -555,7 +595,7 @@ struct BfsApp : gl_app {
   }
 
   PullArgs pull_args() const {
-    return PullArgs{fv.oe_rp, row_end(), fv.oe_col, hub_nbr, fv.ivnum, frag->nonzero_deg};
+    return PullArgs{g_rp, row_end(), g_col, hub_nbr, fv.ivnum, g_nz};
   }
 
   bool fused() const { return cfg.fuse_supersteps && fv.fnum == 1; }
@@ -565,12 +605,13 @@ struct BfsApp : gl_app {
   int RunFused() {
     cudaStream_t s = eng.stream;
     uint32_t src = 0;
-    int has_src = gl_frag_oid2lid(frag, cfg.source_oid, &src) == GL_OK;
-    GL_LAUNCH(k_bfs_seed_fused, 1, 32, s, src, has_src, level_bm(0), vis, fv.oe_rp,
+    int has_src = has_src_;
+    src = src_;   // already translated to the hub-first rank in Setup
+    GL_LAUNCH(k_bfs_seed_fused, 1, 32, s, src, has_src, level_bm(0), vis, g_rp,
               (unsigned long long) frag->oe.entries, d_ctl);
     BfsFusedArgs a;
     a.pa = pull_args();
-    a.er = EdgeRange{fv.oe_rp, fv.oe_col, nullptr};
+    a.er = EdgeRange{g_rp, g_col, nullptr};
     a.lv = lv;
     a.words = (uint32_t) words;
     a.max_lv = max_lv;
@@ -619,10 +660,11 @@ struct BfsApp : gl_app {
   int PEval() override {
     if (fused()) return RunFused();
     uint32_t src;
-    if (gl_frag_oid2lid(frag, cfg.source_oid, &src) == GL_OK) {
+    if (has_src_) {
+      src = src_;
       GL_LAUNCH(k_bfs_seed, 1, 32, eng.stream, src, level_bm(0), vis);
       uint64_t rp2[2];
-      GL_CUDA(cudaMemcpyAsync(rp2, fv.oe_rp + src, sizeof(rp2), cudaMemcpyDeviceToHost, eng.stream));
+      GL_CUDA(cudaMemcpyAsync(rp2, g_rp + src, sizeof(rp2), cudaMemcpyDeviceToHost, eng.stream));
       GL_CUDA(cudaStreamSynchronize(eng.stream));
       n_f = 1;
       m_f = rp2[1] - rp2[0];
@@ -652,7 +694,7 @@ struct BfsApp : gl_app {
     if (multi) {
       // ParallelProcess (bfs.h:158-166): received vertices join the current level
       MsgView mv = mm.view();
-      BfsApply ap{cur, vis, fv.oe_rp};
+      BfsApply ap{cur, vis, g_rp};
       GL_LAUNCH((k_unpack<ItemU32, BfsApply>), eng.sm_count * 4, kTB, s, mv, ap, eng.ctrl);
       GL_TRY(eng.reset_ctrl());
       GL_CUDA(cudaMemsetAsync(remote, 0, sizeof(uint32_t) * words, s));
@@ -670,12 +712,12 @@ struct BfsApp : gl_app {
       phase = (n_f >= g_vnum / 24) ? 1 : 2;
     }
     const bool use_pull = phase == 1;
-    EdgeRange er{fv.oe_rp, fv.oe_col, nullptr};
+    EdgeRange er{g_rp, g_col, nullptr};
     if (!use_pull) {
       // leaving the pull phase: outer copies learn which vertices their owners
       // visited meanwhile, so the push phase does not re-report them
       if (multi && prev_phase == 1) GL_TRY(mm.SyncBitsToGhosts(s, vis));
-      OpBfsPush op{vis, nxt, remote, fv.oe_rp, fv.ivnum};
+      OpBfsPush op{vis, nxt, remote, g_rp, fv.ivnum};
       GL_TRY(run_frontier_scan(eng, cur, fv.ivnum, er, op));
       if (multi) {
         MsgView mv = mm.view();
@@ -734,7 +776,7 @@ struct BfsApp : gl_app {
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
     uint32_t nl = std::min<uint32_t>(max_lv, used_lv + 1);
-    GL_LAUNCH(k_depth_from_levels, (fv.ivnum + 255) / 256, 256, eng.stream, lv, (uint32_t) words, nl, fv.ivnum, out64);
+    GL_LAUNCH(k_depth_from_levels, (fv.ivnum + 255) / 256, 256, eng.stream, lv, (uint32_t) words, nl, fv.ivnum, perm, out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(int64_t) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
     GL_CUDA(cudaStreamSynchronize(eng.stream));
     return GL_OK;

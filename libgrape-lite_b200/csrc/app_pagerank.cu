@@ -12,7 +12,10 @@
 // cfg.pr_pull = 1 selects a deterministic pull step (single fragment):
 //   next[v] = base + d * sum_{u in N(v)} rank[u]/deg(u)
 // which is the CPU app's formulation (pagerank/pagerank.h:102-154).
+#include <cub/cub.cuh>
+
 #include "apps_common.cuh"
+#include "dense.cuh"
 
 namespace gl {
 namespace {
@@ -58,13 +61,50 @@ __global__ void k_pr_base(double* next, uint32_t ivnum, double base) {
   if (i < ivnum) next[i] = base;
 }
 
-// contrib[u] = rank[u]/deg(u)
+// pull as an edge-balanced dense sweep: next[row] += delta * sum contrib[col]
+struct OpPrPull {
+  using Val = double;
+  using W = float;
+  static constexpr bool kWeighted = false;
+  const double* contrib;
+  double* next;
+  double delta;
+  GL_DEV Val identity() const { return 0.0; }
+  GL_DEV Val entry(uint32_t v, W) const { return __ldcg(contrib + v); }
+  GL_DEV Val combine(Val a, Val b) const { return a + b; }
+  GL_DEV void flush(uint32_t row, Val part, ScanAcc&) const { atomicAdd(next + row, delta * part); }
+};
+
+// contrib[slot(u)] = rank[u]/deg(u).  slot = identity, or the hub-first
+// permutation: the gathered array is then ordered by descending degree, so the
+// few thousand hub entries that receive most of the 5e8 random reads of a
+// sweep are contiguous and stay in L1/L2 (the 134 MB array does not fit L2).
 __global__ void k_pr_contrib(const double* rank, const uint64_t* rp,
-                             uint32_t ivnum, double* contrib) {
+                             uint32_t ivnum, const uint32_t* __restrict__ perm, double* contrib) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < ivnum) {
     uint64_t dg = rp[i + 1] - rp[i];
-    contrib[i] = dg ? rank[i] / (double) dg : 0.0;
+    contrib[perm ? perm[i] : i] = dg ? rank[i] / (double) dg : 0.0;
+  }
+}
+__global__ void k_pr_degkey(const uint64_t* rp, uint32_t n, uint32_t* key, uint32_t* val) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint64_t dg = rp[i + 1] - rp[i];
+    if (dg > 0xFFFFFFFFull) dg = 0xFFFFFFFFull;
+    key[i] = 0xFFFFFFFFu - (uint32_t) dg;   // ascending key = descending degree
+    val[i] = i;
+  }
+}
+__global__ void k_pr_invert(const uint32_t* order, uint32_t n, uint32_t* perm) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) perm[order[i]] = i;
+}
+__global__ void k_pr_permute_cols(const uint32_t* __restrict__ col, uint64_t m,
+                                  const uint32_t* __restrict__ perm, uint32_t n, uint32_t* out) {
+  for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t) gridDim.x * blockDim.x) {
+    uint32_t c = col[i];
+    out[i] = c < n ? perm[c] : c;
   }
 }
 
@@ -132,6 +172,7 @@ __global__ void k_ones(uint32_t* bm, uint32_t nbits, uint32_t words) {
 struct PageRankApp : gl_app {
   double *rank = nullptr, *next = nullptr, *contrib = nullptr, *d_dangling = nullptr;
   uint32_t* all_inner = nullptr;
+  uint32_t *perm = nullptr, *col_p = nullptr;   // hub-first gather order (pull, one fragment)
   size_t words = 0;
   uint32_t tvnum = 0;
   int curr_iter = 0;
@@ -142,6 +183,8 @@ struct PageRankApp : gl_app {
     cudaFree(contrib);
     cudaFree(d_dangling);
     cudaFree(all_inner);
+    cudaFree(perm);
+    cudaFree(col_p);
   }
   size_t ResultElemBytes() const override { return sizeof(double); }
 
@@ -155,9 +198,40 @@ struct PageRankApp : gl_app {
     GL_LAUNCH(k_ones, (unsigned) ((words + 255) / 256), 256, eng.stream, all_inner, fv.ivnum, (uint32_t) words);
     if (cfg.pr_pull) {
       GL_CUDA(cudaMalloc(&contrib, sizeof(double) * std::max<uint32_t>(tvnum, 1)));
+      if (fv.fnum == 1 && fv.ivnum) GL_TRY(BuildHubOrder());
     }
     GL_TRY(mm.Init(comm, fv, sizeof(ItemU32F64)));
     if (cfg.pr_pull && fv.fnum > 1) GL_TRY(mm.BuildMirrorPlan(eng.stream, fv));
+    return GL_OK;
+  }
+
+  // perm[u] = rank of u by descending degree; col_p = perm[col]
+  int BuildHubOrder() {
+    cudaStream_t s = eng.stream;
+    const uint32_t n = fv.ivnum;
+    const uint64_t m = frag->oe.entries;
+    uint32_t *key = nullptr, *key2 = nullptr, *val = nullptr, *val2 = nullptr;
+    GL_CUDA(cudaMalloc(&key, 4ull * n));
+    GL_CUDA(cudaMalloc(&key2, 4ull * n));
+    GL_CUDA(cudaMalloc(&val, 4ull * n));
+    GL_CUDA(cudaMalloc(&val2, 4ull * n));
+    GL_LAUNCH(k_pr_degkey, (n + 255) / 256, 256, s, fv.oe_rp, n, key, val);
+    size_t tb = 0;
+    cub::DoubleBuffer<uint32_t> kb(key, key2), vb(val, val2);
+    GL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (int) n, 0, 32, s));
+    void* tmp = nullptr;
+    GL_CUDA(cudaMalloc(&tmp, std::max<size_t>(tb, 16)));
+    GL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, kb, vb, (int) n, 0, 32, s));
+    GL_CUDA(cudaMalloc(&perm, 4ull * n));
+    GL_LAUNCH(k_pr_invert, (n + 255) / 256, 256, s, vb.Current(), n, perm);
+    GL_CUDA(cudaMalloc(&col_p, 4ull * (m + 16)));
+    if (m) GL_LAUNCH(k_pr_permute_cols, eng.sm_count * 8, 256, s, fv.oe_col, m, perm, n, col_p);
+    GL_CUDA(cudaStreamSynchronize(s));
+    cudaFree(key);
+    cudaFree(key2);
+    cudaFree(val);
+    cudaFree(val2);
+    cudaFree(tmp);
     return GL_OK;
   }
 
@@ -196,12 +270,22 @@ struct PageRankApp : gl_app {
       static thread_local int gp = 0;
       if (!gp) gp = persistent_grid(k_pr_pull, eng.sm_count);
       if (fv.ivnum) {
-        GL_LAUNCH(k_pr_contrib, (fv.ivnum + 255) / 256, 256, s, rank, fv.oe_rp, fv.ivnum, contrib);
+        GL_LAUNCH(k_pr_contrib, (fv.ivnum + 255) / 256, 256, s, rank, fv.oe_rp, fv.ivnum, perm, contrib);
       }
       // outer copies take their owner's contribution (dense mirror sync)
       if (fv.fnum > 1) GL_TRY(mm.SyncValuesToGhosts(s, contrib, 8));
       if (fv.ivnum) {
-        GL_LAUNCH(k_pr_pull, gp, kTB, s, fv.oe_rp, fv.oe_col, contrib, next, fv.ivnum, base, cfg.pr_delta, eng.ctrl);
+        // next = base, then the TMA-staged dense sweep folds the gathered sums in
+        GL_LAUNCH(k_pr_base, (fv.ivnum + 255) / 256, 256, s, next, fv.ivnum, base);
+        static thread_local int gd = 0;
+        if (!gd) gd = persistent_grid(k_dense_pull<OpPrPull>, eng.sm_count);
+        if (frag->oe_ntiles) {
+          OpPrPull op{contrib, next, cfg.pr_delta};
+          int grid = (int) std::min<uint32_t>((uint32_t) gd, frag->oe_ntiles);
+          GL_LAUNCH(k_dense_pull<OpPrPull>, grid, kTB, s, fv.oe_rp, col_p ? col_p : fv.oe_col, (const void*) nullptr, frag->oe_tile_row,
+                    frag->oe_ntiles, fv.ivnum, (uint64_t) frag->oe.entries, op, eng.ctrl);
+        }
+        (void) gp;
       }
     } else {
       if (fv.ivnum) GL_LAUNCH(k_pr_base, (fv.ivnum + 255) / 256, 256, s, next, fv.ivnum, base);

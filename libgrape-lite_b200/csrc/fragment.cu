@@ -14,6 +14,7 @@
 
 #include <algorithm>
 
+#include "dense.cuh"
 #include "fragment.h"
 #include "rmat.h"
 
@@ -528,7 +529,7 @@ int build_from_producer(gl_frag* f, Producer& prod, uint64_t n, int directed,
     out.entries = m;
     GL_CUDA(cudaMalloc(&out.rp, sizeof(uint64_t) * ((size_t) f->ivnum + 1)));
     GL_CUDA(cudaMalloc(&out.split, sizeof(uint64_t) * std::max<size_t>(f->ivnum, 1)));
-    GL_CUDA(cudaMalloc(&out.col, sizeof(uint32_t) * std::max<uint64_t>(m, 4)));
+    GL_CUDA(cudaMalloc(&out.col, sizeof(uint32_t) * (m + 16)));
     k_rowptr<<<nblk((uint64_t) f->ivnum + 1), 256>>>(keys.as<uint64_t>(), m, f->ivnum, out.rp, out.split);
     if (m) k_cols<<<nblk(m), 256>>>(keys.as<uint64_t>(), m, f->ivnum, outer_sorted.as<uint32_t>(), ovnum, out.col);
     GL_COUNT_LAUNCH();
@@ -579,6 +580,12 @@ int finish_common(gl_frag* f) {
   f->max_degree_lid = f->ivnum ? 0xFFFFFFFFu - (uint32_t) hb : 0;
   f->device_bytes += words * 4;
   if (f->ovnum) GL_TRY(build_ovie(f));
+  // tile -> first row table of the dense sweeps
+  f->oe_ntiles = (uint32_t) ((f->oe.entries + kDenseTile - 1) / kDenseTile);
+  GL_CUDA(cudaMalloc(&f->oe_tile_row, sizeof(uint32_t) * ((size_t) f->oe_ntiles + 1)));
+  k_dense_tile_rows<<<nblk((uint64_t) f->oe_ntiles + 1), 256>>>(f->oe.rp, f->ivnum, f->oe.entries, f->oe_ntiles, f->oe_tile_row);
+  GL_COUNT_LAUNCH();
+  f->device_bytes += sizeof(uint32_t) * ((size_t) f->oe_ntiles + 1);
   GL_CUDA(cudaDeviceSynchronize());
   return GL_OK;
 }
@@ -613,7 +620,7 @@ int build_ovie(gl_frag* f) {
   o.entries = m;
   GL_CUDA(cudaMalloc(&o.rp, sizeof(uint64_t) * ((size_t) f->ovnum + 1)));
   GL_CUDA(cudaMalloc(&o.split, sizeof(uint64_t) * std::max<size_t>(f->ovnum, 1)));
-  GL_CUDA(cudaMalloc(&o.col, sizeof(uint32_t) * std::max<uint64_t>(m, 4)));
+  GL_CUDA(cudaMalloc(&o.col, sizeof(uint32_t) * (m + 16)));
   k_rowptr<<<nblk((uint64_t) f->ovnum + 1), 256>>>(keys.as<uint64_t>(), m, f->ovnum, o.rp, o.split);
   if (m) k_low32<<<nblk(m), 256>>>(keys.as<uint64_t>(), m, o.col);
   GL_COUNT_LAUNCH();
@@ -774,7 +781,7 @@ int gl_frag_create(gl_frag_t** out, const gl_frag_desc* d) {
     o.entries = m;
     GL_CUDA(cudaMalloc(&o.rp, sizeof(uint64_t) * (c.rows + 1)));
     GL_CUDA(cudaMemcpy(o.rp, c.row_ptr, sizeof(uint64_t) * (c.rows + 1), cudaMemcpyHostToDevice));
-    GL_CUDA(cudaMalloc(&o.col, sizeof(uint32_t) * std::max<uint64_t>(m, 4)));
+    GL_CUDA(cudaMalloc(&o.col, sizeof(uint32_t) * (m + 16)));
     if (m) GL_CUDA(cudaMemcpy(o.col, c.col, sizeof(uint32_t) * m, cudaMemcpyHostToDevice));
     if (has_w && c.edata && m) {
       GL_CUDA(cudaMalloc(&o.w, (size_t) d->edata_bytes * m));
@@ -923,7 +930,7 @@ int gl_frag_offload(gl_frag_t* f) {
 int gl_frag_reload(gl_frag_t* f) {
   GL_ARG(f, "null argument");
   if (!f->offloaded) return GL_OK;
-  GL_CUDA(cudaMalloc(&f->oe.col, sizeof(uint32_t) * std::max<uint64_t>(f->oe.entries, 4)));
+  GL_CUDA(cudaMalloc(&f->oe.col, sizeof(uint32_t) * (f->oe.entries + 16)));
   if (f->oe.entries) GL_CUDA(cudaMemcpy(f->oe.col, f->sh_col.data(), sizeof(uint32_t) * f->oe.entries, cudaMemcpyHostToDevice));
   if (!f->sh_w.empty()) {
     GL_CUDA(cudaMalloc(&f->oe.w, f->sh_w.size()));
@@ -953,6 +960,7 @@ void gl_frag_destroy(gl_frag_t* f) {
   if (f->outer_range) cudaFree(f->outer_range);
   if (f->inner_oids) cudaFree(f->inner_oids);
   if (f->nonzero_deg) cudaFree(f->nonzero_deg);
+  if (f->oe_tile_row) cudaFree(f->oe_tile_row);
   delete f;
 }
 

@@ -37,6 +37,9 @@ struct gl_frag {
   uint64_t part_chunk = 0;  // ceil(n/fnum) of the segmented partitioner (0 = unknown)
   // bitmap of inner vertices with out-degree > 0 (pull candidates)
   uint32_t* nonzero_deg = nullptr;
+  // dense sweeps (dense.cuh): first row touching each 4096-entry tile of oe.col
+  uint32_t* oe_tile_row = nullptr;
+  uint32_t oe_ntiles = 0;
   uint64_t device_bytes = 0;
   uint32_t max_degree = 0, max_degree_lid = 0;
   bool offloaded = false;
