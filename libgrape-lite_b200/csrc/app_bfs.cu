@@ -30,7 +30,7 @@
 namespace cg = cooperative_groups;
 
 #ifndef GL_BFS_FUSED_CTAS
-#define GL_BFS_FUSED_CTAS 8
+#define GL_BFS_FUSED_CTAS 4
 #endif
 
 namespace gl {
@@ -66,6 +66,13 @@ __global__ void k_bfs_nz(const uint64_t* rp, uint32_t n, uint32_t* nz) {
   bool has = i < n && rp[i + 1] > rp[i];
   uint32_t w = __ballot_sync(0xffffffffu, has);
   if ((threadIdx.x & 31) == 0 && i < n) nz[i >> 5] = w;
+}
+
+__global__ void k_bfs_popc(const uint32_t* bm, uint32_t words, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) c += __popc(bm[i]);
+  c = warp_sum(c);
+  if (lane_id() == 0 && c) atomicAdd(out, c);
 }
 
 __global__ void k_bfs_seed(uint32_t src, uint32_t* lv0, uint32_t* vis) {
@@ -256,7 +263,7 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
   if (threadIdx.x == 0 && cand) atomicAdd(&ctrl->frontier, (unsigned long long) cand);
 }
 
-__global__ void __launch_bounds__(kTB, 8)
+__global__ void __launch_bounds__(kTB, 4)
 k_bfs_pull(PullArgs a, const uint32_t* __restrict__ cur, uint32_t* vis,
            uint32_t* nxt, ScanCtrl* ctrl) {
   __shared__ PullSmem sm;
@@ -336,10 +343,18 @@ GL_DEV unsigned long long global_ns() {
 // 2 = final push.
 GL_DEV uint32_t bfs_next_phase(uint32_t phase, unsigned long long n_f,
                                unsigned long long m_f, unsigned long long m_u,
-                               uint32_t ivnum, int direction_opt) {
+                               uint32_t ivnum, int direction_opt, uint32_t beta,
+                               unsigned long long unvisited_nz) {
   if (!direction_opt) return 0;
   if (phase == 0) return m_f > m_u / 14 ? 1u : 0u;
-  if (phase == 1) return n_f >= (unsigned long long) ivnum / 24 ? 1u : 2u;
+  if (phase == 1) {
+    // A pull level costs ~ the unvisited non-isolated vertices, a push level
+    // ~ the frontier's edges plus two grid barriers: keep pulling while the
+    // frontier is large (Beamer) or while few candidates remain per frontier
+    // vertex (the tail of a skewed graph); go back to push for long sparse tails.
+    if (n_f >= (unsigned long long) ivnum / beta) return 1u;
+    return unvisited_nz <= 64ull * n_f ? 1u : 2u;
+  }
   return 2u;
 }
 
@@ -373,6 +388,8 @@ struct BfsFusedArgs {
   uint32_t max_lv;   // number of level bitmaps available
   uint32_t* vis;
   int direction_opt;
+  uint32_t beta;     // pull -> push when n_f < V / beta ...
+  unsigned long long nz_total;  // ... and many non-isolated vertices are still unvisited
   BfsFusedCtl* ctl;
   HubItem* hubs;
   uint32_t hub_cap, hub_deg;
@@ -396,7 +413,8 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedAr
   unsigned long long m_f = ctl->src_deg;
   unsigned long long visited_edges = m_f;
   const unsigned long long m_total = ctl->m_total;
-  uint32_t phase = bfs_next_phase(0, n_f, m_f, m_total - visited_edges, a.pa.ivnum, a.direction_opt);
+  unsigned long long visited_cnt = n_f;
+  uint32_t phase = bfs_next_phase(0, n_f, m_f, m_total - visited_edges, a.pa.ivnum, a.direction_opt, a.beta, a.nz_total);
   for (uint32_t depth = 0; n_f != 0; ++depth) {
     if (depth + 1 >= a.max_lv) {
       if (gtid == 0) ctl->overflow = 1;
@@ -436,9 +454,11 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedAr
     n_f = next_count;
     m_f = next_edges;
     visited_edges += next_edges;
+    visited_cnt += next_count;
     phase = bfs_next_phase(phase, n_f, m_f,
                            m_total > visited_edges ? m_total - visited_edges : 0,
-                           a.pa.ivnum, a.direction_opt);
+                           a.pa.ivnum, a.direction_opt, a.beta,
+                           a.nz_total > visited_cnt ? a.nz_total - visited_cnt : 0);
   }
 }
 
@@ -489,6 +509,7 @@ struct BfsApp : gl_app {
   uint64_t* rp_p = nullptr;
   uint32_t src_ = 0;
   int has_src_ = 0;
+  unsigned long long nz_total = 0, visited_cnt = 0;
   size_t words = 0;
   uint32_t tvnum = 0;
   uint32_t max_lv = 0;
@@ -559,6 +580,15 @@ struct BfsApp : gl_app {
     }
     if (fv.ivnum && can_pull())
       GL_LAUNCH(k_bfs_hub_nbr, eng.sm_count * 8, 256, eng.stream, g_rp, row_end(), g_col, fv.ivnum, hub_nbr);
+    {
+      unsigned long long* d_cnt = nullptr;
+      GL_CUDA(cudaMalloc(&d_cnt, 8));
+      GL_CUDA(cudaMemsetAsync(d_cnt, 0, 8, eng.stream));
+      GL_LAUNCH(k_bfs_popc, eng.sm_count * 4, 256, eng.stream, g_nz, (uint32_t) bm_words(fv.ivnum), d_cnt);
+      GL_CUDA(cudaMemcpyAsync(&nz_total, d_cnt, 8, cudaMemcpyDeviceToHost, eng.stream));
+      GL_CUDA(cudaStreamSynchronize(eng.stream));
+      cudaFree(d_cnt);
+    }
     // the source is fixed per app (AppConfig): resolve it once
     has_src_ = gl_frag_oid2lid(frag, cfg.source_oid, &src_) == GL_OK ? 1 : 0;
     if (has_src_ && perm) GL_CUDA(cudaMemcpy(&src_, perm + src_, 4, cudaMemcpyDeviceToHost));
@@ -588,6 +618,7 @@ struct BfsApp : gl_app {
     curr_depth = 0;
     used_lv = 0;
     n_f = m_f = visited_edges = 0;
+    visited_cnt = 1;
     phase = 0;
     rounds_noted = false;
     pending_stats = false;
@@ -617,6 +648,8 @@ struct BfsApp : gl_app {
     a.max_lv = max_lv;
     a.vis = vis;
     a.direction_opt = can_pull() ? 1 : 0;
+    a.beta = cfg.reserved[2] > 0 ? (uint32_t) cfg.reserved[2] : 24u;
+    a.nz_total = nz_total;
     a.ctl = d_ctl;
     a.hubs = eng.hubs;
     a.hub_cap = eng.hub_cap;
@@ -709,7 +742,8 @@ struct BfsApp : gl_app {
     } else if (phase == 0) {
       phase = (n_f > 0 && m_f > m_u / 14) ? 1 : 0;
     } else if (phase == 1) {
-      phase = (n_f >= g_vnum / 24) ? 1 : 2;
+      const uint64_t unvis = nz_total > visited_cnt ? nz_total - visited_cnt : 0;
+      phase = (n_f >= g_vnum / 24) ? 1 : ((fv.fnum == 1 && unvis <= 64 * n_f) ? 1 : 2);
     }
     const bool use_pull = phase == 1;
     EdgeRange er{g_rp, g_col, nullptr};
@@ -749,6 +783,7 @@ struct BfsApp : gl_app {
       n_f = c.next_count;
       m_f = c.next_edges;
       visited_edges += c.next_edges;
+      visited_cnt += c.next_count;
     }
     ++curr_depth;
     used_lv = curr_depth + 1;
