@@ -84,11 +84,12 @@ def _rmat_file(scale, edgefactor, seed, weighted):
     return _graph_cache[key]
 
 
-def run(exe, app, scale, edgefactor=16, seed=1):
-    """bench.py CPU arm: one query of the reference CPU app with all host threads."""
+def run(exe, app, scale, edgefactor=16, seed=1, repeat=1, keep=1):
+    """bench.py CPU arm: `repeat` queries of the reference CPU app in ONE process
+    (graph loaded once), all host threads; the mean of the last `keep` is reported."""
     path, source, m = _rmat_file(scale, edgefactor, seed, app == "sssp")
-    info, text = run_app(app, path, source=source, repeat=1, want_output=(app in ("bfs", "sssp")))
-    ms = float(info["query_ms"][-1])
+    info, text = run_app(app, path, source=source, repeat=repeat, want_output=(app in ("bfs", "sssp")))
+    ms = float(np.mean(info["query_ms"][-keep:]))
     if app in ("bfs", "sssp"):
         # Graph500 numerator: input edges with a reached endpoint
         _, vals = parse_output(text, float if app == "sssp" else int)
@@ -101,7 +102,7 @@ def run(exe, app, scale, edgefactor=16, seed=1):
     else:
         edges = m
     return {"value": edges / (ms * 1e-3), "unit": "edges/s", "ms": ms, "cores": int(info["threads"]),
-            "kind": "reference",
+            "kind": "reference", "all_ms": [float(x) for x in info["query_ms"]], "load_s": info["load_s"],
             "sample": "%s on R-MAT scale-%d (same generator/seed as the GPU arm), one Query() of the "
                       "unmodified reference CPU app (ParallelEngine, %d threads of %d)"
                       % (app.upper(), scale, info["threads"], info["hardware_concurrency"])}
