@@ -79,7 +79,8 @@ namespace gl {
 // hub-first (descending degree) order of the inner vertices: perm[lid] = rank, order[rank] = lid
 int build_hub_order(cudaStream_t s, const uint64_t* rp, uint32_t n, uint32_t** perm_out, uint32_t** order_out);
 int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, uint64_t m, uint32_t n,
-                       const uint32_t* order, const uint32_t* perm, uint64_t** rp_out, uint32_t** col_out);
+                       const uint32_t* order, const uint32_t* perm, uint64_t** rp_out, uint32_t** col_out,
+                       const void* w4 = nullptr, void** w4_out = nullptr);
 gl_app* make_bfs();
 gl_app* make_sssp_f32();
 gl_app* make_sssp_f64();

@@ -35,7 +35,8 @@ __global__ void k_perm_deg(const uint64_t* rp, const uint32_t* order, uint32_t n
 __global__ void __launch_bounds__(256)
 k_perm_rows(const uint64_t* __restrict__ rp, const uint32_t* __restrict__ col,
             const uint32_t* __restrict__ order, const uint32_t* __restrict__ perm,
-            uint32_t n, const uint64_t* __restrict__ rp_p, uint32_t* col_p) {
+            uint32_t n, const uint64_t* __restrict__ rp_p, uint32_t* col_p,
+            const uint32_t* __restrict__ w, uint32_t* w_p) {
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
     const uint32_t u = order[i];
@@ -43,6 +44,7 @@ k_perm_rows(const uint64_t* __restrict__ rp, const uint32_t* __restrict__ col,
     for (uint64_t p = b + lane_id(); p < e; p += 32) {
       const uint32_t c = col[p];
       col_p[o + (p - b)] = c < n ? perm[c] : c;
+      if (w) w_p[o + (p - b)] = w[p];   // 4-byte edge data moves with its edge
     }
   }
 }
@@ -77,7 +79,8 @@ int build_hub_order(cudaStream_t s, const uint64_t* rp, uint32_t n, uint32_t** p
 
 // rows reordered by `order`, neighbours relabelled by `perm`
 int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, uint64_t m, uint32_t n,
-                       const uint32_t* order, const uint32_t* perm, uint64_t** rp_out, uint32_t** col_out) {
+                       const uint32_t* order, const uint32_t* perm, uint64_t** rp_out, uint32_t** col_out,
+                       const void* w4, void** w4_out) {
   uint64_t *deg = nullptr, *rp_p = nullptr;
   GL_CUDA(cudaMalloc(&deg, 8ull * ((size_t) n + 1)));
   GL_CUDA(cudaMalloc(&rp_p, 8ull * ((size_t) n + 1)));
@@ -89,7 +92,9 @@ int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, 
   GL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, deg, rp_p, (int) (n + 1), s));
   uint32_t* col_p = nullptr;
   GL_CUDA(cudaMalloc(&col_p, 4ull * (m + 16)));
-  if (n) GL_LAUNCH(k_perm_rows, 148 * 8, 256, s, rp, col, order, perm, n, rp_p, col_p);
+  uint32_t* w_p = nullptr;
+  if (w4) GL_CUDA(cudaMalloc(&w_p, 4ull * (m + 16)));
+  if (n) GL_LAUNCH(k_perm_rows, 148 * 8, 256, s, rp, col, order, perm, n, rp_p, col_p, (const uint32_t*) w4, w_p);
   // rows sorted by the new ids = by descending degree of the neighbour: the
   // most promising parents come first in a pull scan, and the entries of a
   // row that fall into the same bitmap word are adjacent
@@ -97,10 +102,21 @@ int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, 
     uint32_t* sorted = nullptr;
     GL_CUDA(cudaMalloc(&sorted, 4ull * (m + 16)));
     size_t sb = 0;
-    GL_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, sb, col_p, sorted, (int64_t) m, (int64_t) n, rp_p, rp_p + 1, s));
     void* st = nullptr;
-    GL_CUDA(cudaMalloc(&st, std::max<size_t>(sb, 16)));
-    GL_CUDA(cub::DeviceSegmentedSort::SortKeys(st, sb, col_p, sorted, (int64_t) m, (int64_t) n, rp_p, rp_p + 1, s));
+    if (!w_p) {
+      GL_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, sb, col_p, sorted, (int64_t) m, (int64_t) n, rp_p, rp_p + 1, s));
+      GL_CUDA(cudaMalloc(&st, std::max<size_t>(sb, 16)));
+      GL_CUDA(cub::DeviceSegmentedSort::SortKeys(st, sb, col_p, sorted, (int64_t) m, (int64_t) n, rp_p, rp_p + 1, s));
+    } else {
+      uint32_t* w_sorted = nullptr;
+      GL_CUDA(cudaMalloc(&w_sorted, 4ull * (m + 16)));
+      GL_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, sb, col_p, sorted, w_p, w_sorted, (int64_t) m, (int64_t) n, rp_p, rp_p + 1, s));
+      GL_CUDA(cudaMalloc(&st, std::max<size_t>(sb, 16)));
+      GL_CUDA(cub::DeviceSegmentedSort::SortPairs(st, sb, col_p, sorted, w_p, w_sorted, (int64_t) m, (int64_t) n, rp_p, rp_p + 1, s));
+      GL_CUDA(cudaStreamSynchronize(s));
+      cudaFree(w_p);
+      w_p = w_sorted;
+    }
     GL_CUDA(cudaStreamSynchronize(s));
     cudaFree(st);
     cudaFree(col_p);
@@ -111,6 +127,7 @@ int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, 
   cudaFree(tmp);
   *rp_out = rp_p;
   *col_out = col_p;
+  if (w4_out) *w4_out = w_p;
   return GL_OK;
 }
 
