@@ -314,6 +314,10 @@ class App:
                 v = GL_LB[v]
             if not hasattr(c, k):
                 raise GrapeError("unknown app config key %r" % k)
+            if k == "reserved":          # {index: value}
+                for i, x in dict(v).items():
+                    c.reserved[int(i)] = int(x)
+                continue
             setattr(c, k, v)
         self.cfg = c
         self.h = C.c_void_p()

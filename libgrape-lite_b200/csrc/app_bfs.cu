@@ -327,6 +327,13 @@ struct BfsFusedCtl {
   uint32_t pad;
   unsigned long long src_deg, m_total, touched;
   unsigned long long t_begin;
+  // state the kernel starts from: written by the seed kernel, and by the
+  // kernel itself when it stops because the level-bitmap ring is full (the
+  // host spills the finished levels and relaunches)
+  unsigned long long r_nf, r_mf, r_visited_edges, r_visited_cnt;
+  uint32_t r_phase, r_pad;   // r_phase = ~0: derive from the seed
+  unsigned long long p_nf, p_mf, p_visited_edges, p_visited_cnt;   // parked state (-> r_* by k_bfs_resume_prep)
+  uint32_t p_phase, p_pad;
   BfsLevelStat stat[kMaxFusedStats];
 };
 
@@ -377,7 +384,41 @@ __global__ void k_bfs_seed_fused(uint32_t src, int has_src, uint32_t* lv0,
   }
   ctl->has_src = has_src;
   ctl->src_deg = deg;
+  ctl->r_nf = has_src ? 1 : 0;
+  ctl->r_mf = deg;
+  ctl->r_visited_edges = deg;
+  ctl->r_visited_cnt = has_src ? 1 : 0;
+  ctl->r_phase = 0xFFFFFFFFu;
   ctl->t_begin = global_ns();
+}
+
+// between two launches of a spilled query: fresh level counters
+__global__ void k_bfs_resume_prep(BfsFusedCtl* ctl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->c[0] = ScanCtrl();
+  ctl->c[1] = ScanCtrl();
+  ctl->c[2] = ScanCtrl();
+  ctl->overflow = 0;
+  ctl->r_nf = ctl->p_nf;
+  ctl->r_mf = ctl->p_mf;
+  ctl->r_visited_edges = ctl->p_visited_edges;
+  ctl->r_visited_cnt = ctl->p_visited_cnt;
+  ctl->r_phase = ctl->p_phase;
+}
+
+// Spill: depth of every vertex found in ring levels [0, nlevels) goes to the
+// int32 side array (absolute depth = base + ring index).
+__global__ void k_bfs_spill(const uint32_t* lv, uint32_t words, uint32_t nlevels, uint32_t n,
+                            uint32_t base, int32_t* spill) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t w = i >> 5, m = 1u << (i & 31);
+  for (uint32_t l = 0; l < nlevels; ++l) {
+    if (lv[(size_t) l * words + w] & m) {
+      spill[i] = (int32_t) (base + l);
+      break;
+    }
+  }
 }
 
 struct BfsFusedArgs {
@@ -386,6 +427,7 @@ struct BfsFusedArgs {
   uint32_t* lv;      // level bitmaps: lv + d*words
   uint32_t words;
   uint32_t max_lv;   // number of level bitmaps available
+  uint32_t depth_base;  // absolute depth of ring level 0 (> 0 after a spill)
   uint32_t* vis;
   int direction_opt;
   uint32_t beta;     // pull -> push when n_f < V / beta ...
@@ -409,15 +451,25 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedAr
   BfsFusedCtl* ctl = a.ctl;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
   // running totals, replicated in every thread
-  unsigned long long n_f = ctl->has_src ? 1 : 0;
-  unsigned long long m_f = ctl->src_deg;
-  unsigned long long visited_edges = m_f;
+  unsigned long long n_f = ctl->r_nf;
+  unsigned long long m_f = ctl->r_mf;
+  unsigned long long visited_edges = ctl->r_visited_edges;
   const unsigned long long m_total = ctl->m_total;
-  unsigned long long visited_cnt = n_f;
-  uint32_t phase = bfs_next_phase(0, n_f, m_f, m_total - visited_edges, a.pa.ivnum, a.direction_opt, a.beta, a.nz_total);
+  unsigned long long visited_cnt = ctl->r_visited_cnt;
+  uint32_t phase = ctl->r_phase;
+  if (phase == 0xFFFFFFFFu)
+    phase = bfs_next_phase(0, n_f, m_f, m_total - visited_edges, a.pa.ivnum, a.direction_opt, a.beta, a.nz_total);
   for (uint32_t depth = 0; n_f != 0; ++depth) {
     if (depth + 1 >= a.max_lv) {
-      if (gtid == 0) ctl->overflow = 1;
+      // ring full: park the state; the host spills levels [0, max_lv-1) and relaunches
+      if (gtid == 0) {
+        ctl->overflow = 1;
+        ctl->p_nf = n_f;
+        ctl->p_mf = m_f;
+        ctl->p_visited_edges = visited_edges;
+        ctl->p_visited_cnt = visited_cnt;
+        ctl->p_phase = phase;
+      }
       break;
     }
     ScanCtrl* C = &ctl->c[depth % 3];
@@ -438,15 +490,16 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedAr
     const unsigned long long next_count = VC->next_count;
     const unsigned long long next_edges = VC->next_edges;
     if (gtid == 0) {
-      if (depth < (uint32_t) kMaxFusedStats) {
+      const uint32_t adepth = a.depth_base + depth;
+      if (adepth < (uint32_t) kMaxFusedStats) {
         BfsLevelStat ls;
         ls.t_ns = global_ns();
         ls.scanned = VC->scanned;
         ls.frontier = (uint32_t) (n_f > 0xFFFFFFFFull ? 0xFFFFFFFFull : n_f);
         ls.mode = phase == 1 ? 1u : 0u;
-        ctl->stat[depth] = ls;
+        ctl->stat[adepth] = ls;
       }
-      ctl->levels = depth + 1;
+      ctl->levels = adepth + 1;
       ctl->touched += VC->touched;
       // c[(depth+2)%3] was last read right after the previous level's barrier
       ctl->c[(depth + 2) % 3] = ScanCtrl();
@@ -481,16 +534,22 @@ struct BfsApply {
 
 // depth[v] = first level whose bitmap holds v (coalesced: a warp shares words)
 // (perm != null: the bitmaps are indexed by the hub-first rank of the vertex)
+// (spill != null: levels older than `base` were moved to the side array)
 __global__ void k_depth_from_levels(const uint32_t* lv, uint32_t words,
-                                    uint32_t nlevels, uint32_t n, const uint32_t* perm, int64_t* out) {
+                                    uint32_t nlevels, uint32_t n, const uint32_t* perm,
+                                    uint32_t base, const int32_t* spill, int64_t* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int64_t d = INT64_MAX;
   const uint32_t pi = perm ? perm[i] : i;
   const uint32_t w = pi >> 5, m = 1u << (pi & 31);
+  if (spill && spill[pi] >= 0) {
+    out[i] = spill[pi];
+    return;
+  }
   for (uint32_t l = 0; l < nlevels; ++l) {
     if (lv[(size_t) l * words + w] & m) {
-      d = (int64_t) l;
+      d = (int64_t) base + l;
       break;
     }
   }
@@ -533,6 +592,7 @@ struct BfsApp : gl_app {
     cudaFree(out64);
     cudaFree(perm);
     cudaFree(order);
+    cudaFree(spill);
     cudaFree(nz_p);
     cudaFree(col_p);
     cudaFree(rp_p);
@@ -554,6 +614,7 @@ struct BfsApp : gl_app {
     // one bitmap per BFS level: up to 1 GiB of them, at most 4096
     size_t budget = (size_t) 1 << 30;
     max_lv = (uint32_t) std::max<size_t>(16, std::min<size_t>(4096, budget / (words * 4)));
+    if (cfg.reserved[3] >= 4) max_lv = (uint32_t) cfg.reserved[3];   // test hook: tiny ring => spills
     GL_CUDA(cudaMalloc(&lv, sizeof(uint32_t) * words * max_lv));
     GL_CUDA(cudaMemsetAsync(lv, 0, sizeof(uint32_t) * words * max_lv, eng.stream));
     GL_CUDA(cudaMalloc(&vis, sizeof(uint32_t) * words));
@@ -611,8 +672,11 @@ struct BfsApp : gl_app {
 
   int Init() override {
     cudaStream_t s = eng.stream;
-    uint32_t dirty = std::min<uint32_t>(max_lv, used_lv + 2);
+    uint32_t dirty = spilled ? max_lv : std::min<uint32_t>(max_lv, used_lv + 2);
     GL_CUDA(cudaMemsetAsync(lv, 0, sizeof(uint32_t) * words * dirty, s));
+    if (spilled) GL_CUDA(cudaMemsetAsync(spill, 0xFF, sizeof(int32_t) * std::max<uint32_t>(fv.ivnum, 1), s));
+    spilled = false;
+    depth_base = 0;
     GL_CUDA(cudaMemsetAsync(vis, 0, sizeof(uint32_t) * words, s));
     GL_CUDA(cudaMemsetAsync(remote, 0, sizeof(uint32_t) * words, s));
     curr_depth = 0;
@@ -622,6 +686,28 @@ struct BfsApp : gl_app {
     phase = 0;
     rounds_noted = false;
     pending_stats = false;
+    return GL_OK;
+  }
+
+  // The level-bitmap ring is full (ring level max_lv-1 holds the unprocessed
+  // frontier): move the depths of ring levels [0, max_lv-1) to the int32 side
+  // array, restart the ring with the frontier at level 0.  BFS depth is then
+  // only bounded by int32 like the reference's depth array (bfs.h:31).
+  int32_t* spill = nullptr;
+  bool spilled = false;
+  uint32_t depth_base = 0;
+  int SpillRing() {
+    cudaStream_t s = eng.stream;
+    if (!spill) {
+      GL_CUDA(cudaMalloc(&spill, sizeof(int32_t) * std::max<uint32_t>(fv.ivnum, 1)));
+      GL_CUDA(cudaMemsetAsync(spill, 0xFF, sizeof(int32_t) * std::max<uint32_t>(fv.ivnum, 1), s));
+    }
+    if (fv.ivnum)
+      GL_LAUNCH(k_bfs_spill, (fv.ivnum + 255) / 256, 256, s, lv, (uint32_t) words, max_lv - 1, fv.ivnum, depth_base, spill);
+    GL_CUDA(cudaMemcpyAsync(lv, level_bm(max_lv - 1), sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, s));
+    GL_CUDA(cudaMemsetAsync(level_bm(1), 0, sizeof(uint32_t) * words * (max_lv - 1), s));
+    depth_base += max_lv - 1;
+    spilled = true;
     return GL_OK;
   }
 
@@ -655,16 +741,19 @@ struct BfsApp : gl_app {
     a.hub_cap = eng.hub_cap;
     a.hub_deg = eng.hub_deg;
     if (!fused_grid) fused_grid = persistent_grid(k_bfs_fused, eng.sm_count);
-    void* args[] = {&a};
-    GL_CUDA(cudaLaunchCooperativeKernel((void*) k_bfs_fused, dim3(fused_grid), dim3(kTB), args, 0, s));
-    GL_COUNT_LAUNCH();
-    GL_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BfsFusedCtl), cudaMemcpyDeviceToHost, s));
-    GL_CUDA(cudaStreamSynchronize(s));
-    used_lv = h_ctl->levels + 1;
-    if (h_ctl->overflow) {
-      set_error("BFS deeper than %u levels: level-bitmap storage exhausted", max_lv);
-      return GL_ERR_STATE;
+    for (;;) {
+      a.depth_base = depth_base;
+      void* args[] = {&a};
+      GL_CUDA(cudaLaunchCooperativeKernel((void*) k_bfs_fused, dim3(fused_grid), dim3(kTB), args, 0, s));
+      GL_COUNT_LAUNCH();
+      GL_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BfsFusedCtl), cudaMemcpyDeviceToHost, s));
+      GL_CUDA(cudaStreamSynchronize(s));
+      if (!h_ctl->overflow) break;
+      // deeper than the ring: spill and resume (high-diameter graphs)
+      GL_TRY(SpillRing());
+      GL_LAUNCH(k_bfs_resume_prep, 1, 32, s, d_ctl);
     }
+    used_lv = h_ctl->levels - depth_base + 1;
     q_touched += h_ctl->touched;
     for (uint32_t i = 0; i < h_ctl->levels && i < (uint32_t) kMaxFusedStats; ++i)
       note_step(h_ctl->stat[i].scanned, h_ctl->stat[i].frontier, (int) h_ctl->stat[i].mode);
@@ -716,12 +805,9 @@ struct BfsApp : gl_app {
 
   int IncEval() override {
     cudaStream_t s = eng.stream;
-    if (curr_depth + 1 >= max_lv) {
-      set_error("BFS deeper than %u levels: level-bitmap storage exhausted", max_lv);
-      return GL_ERR_STATE;
-    }
-    uint32_t* cur = level_bm(curr_depth);
-    uint32_t* nxt = level_bm(curr_depth + 1);
+    if (curr_depth - depth_base + 1 >= max_lv) GL_TRY(SpillRing());
+    uint32_t* cur = level_bm(curr_depth - depth_base);
+    uint32_t* nxt = level_bm(curr_depth - depth_base + 1);
     GL_TRY(eng.reset_ctrl());
     const bool multi = fv.fnum > 1;
     if (multi) {
@@ -786,7 +872,7 @@ struct BfsApp : gl_app {
       visited_cnt += c.next_count;
     }
     ++curr_depth;
-    used_lv = curr_depth + 1;
+    used_lv = curr_depth - depth_base + 1;
     return GL_OK;
   }
 
@@ -811,7 +897,8 @@ struct BfsApp : gl_app {
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
     uint32_t nl = std::min<uint32_t>(max_lv, used_lv + 1);
-    GL_LAUNCH(k_depth_from_levels, (fv.ivnum + 255) / 256, 256, eng.stream, lv, (uint32_t) words, nl, fv.ivnum, perm, out64);
+    GL_LAUNCH(k_depth_from_levels, (fv.ivnum + 255) / 256, 256, eng.stream, lv, (uint32_t) words, nl, fv.ivnum, perm,
+              depth_base, spilled ? spill : nullptr, out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(int64_t) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
     GL_CUDA(cudaStreamSynchronize(eng.stream));
     return GL_OK;

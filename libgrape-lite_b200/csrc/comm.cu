@@ -1,4 +1,5 @@
 // comm.cu — landing-area allocation / CUDA-IPC mapping and the round protocol.
+#include <cstring>
 #include "comm.h"
 #include "engine.cuh"
 #include "apps_common.cuh"
@@ -185,6 +186,38 @@ int MessageManager::PeerBarrierAsync(cudaStream_t s) {
   if (!d_scratch_result) GL_CUDA(cudaMalloc(&d_scratch_result, sizeof(PeerSlot)));
   GL_LAUNCH(k_peer_allreduce, 1, GL_MAX_FNUM, s, fnum, fid, d_peer_slot[par], local, tag, 0ll, 0ll, 0.0, 0,
             nullptr, nullptr, nullptr, d_scratch_result, 0ll, 0ll, nullptr, nullptr);
+  return GL_OK;
+}
+
+int MessageManager::ExchangeBlobs(cudaStream_t s, const void* mine, size_t bytes, std::vector<char>* all) {
+  all->assign(bytes * fnum, 0);
+  if (fnum == 1) {
+    memcpy(all->data(), mine, bytes);
+    return GL_OK;
+  }
+  if (bytes > comm->landing_bytes) {
+    set_error("ExchangeBlobs: %zu bytes exceed the landing slot", bytes);
+    return GL_ERR_COMM;
+  }
+  GL_TRY(PeerBarrier(s));   // nobody still reads parity-0 slots of an earlier exchange
+  for (uint32_t p = 0; p < fnum; ++p) {
+    if (p == fid) continue;
+    char* dst = comm->peer_base[p] + GL_COMM_HEADER + (size_t) fid * comm->landing_bytes;   // (parity 0, src = me)
+    GL_CUDA(cudaMemcpyAsync(dst, mine, bytes, cudaMemcpyHostToDevice, s));
+  }
+  GL_CUDA(cudaStreamSynchronize(s));
+  GL_TRY(PeerBarrier(s));
+  for (uint32_t p = 0; p < fnum; ++p) {
+    if (p == fid) {
+      memcpy(all->data() + (size_t) p * bytes, mine, bytes);
+      continue;
+    }
+    GL_CUDA(cudaMemcpyAsync(all->data() + (size_t) p * bytes,
+                            comm->local_base + GL_COMM_HEADER + (size_t) p * comm->landing_bytes, bytes,
+                            cudaMemcpyDeviceToHost, s));
+  }
+  GL_CUDA(cudaStreamSynchronize(s));
+  GL_TRY(PeerBarrier(s));
   return GL_OK;
 }
 

@@ -106,6 +106,10 @@ struct MessageManager {
   int PeerBarrier(cudaStream_t s);
   // barrier only: enqueued on the stream, no host synchronisation
   int PeerBarrierAsync(cudaStream_t s);
+  // all-gather of one small host blob per rank through the landing area
+  // (bytes <= landing_bytes; only between rounds, when no message slot of
+  // parity 0 is in flight): all[p*bytes ..] = rank p's blob
+  int ExchangeBlobs(cudaStream_t s, const void* mine, size_t bytes, std::vector<char>* all);
   // When set, FinishARound's kernel takes the vote straight from the engine's
   // device counters (force_continue |= next_count > 0, statistics = next_count
   // + remote_count, next_edges) and mirrors the control block to `vote_h_ctrl`,

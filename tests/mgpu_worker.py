@@ -30,7 +30,7 @@ def main():
         dist.all_gather_object(out, arr)
         return np.concatenate(out)
 
-    for wmode, apps in ((0, ["bfs", "bfs_push", "wcc", "pagerank", "pagerank_pull", "cdlp"]), (1, ["sssp"])):
+    for wmode, apps in ((0, ["bfs", "bfs_push", "wcc", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp"])):
         n = 1 << scale
         frag = pkg.Fragment.rmat(scale, 16, seed=17, weight_mode=wmode, fid=rank, fnum=world)
         comm = gdist.make_comm(rank, world, frag.ivnum)
@@ -69,6 +69,8 @@ def main():
                     ok = np.array_equal(got, g.wcc()[0].astype(np.int64))
                 elif kind == "cdlp":
                     ok = np.array_equal(got, g.cdlp(5))
+                elif kind == "lcc":
+                    ok = np.array_equal(got, g.lcc()[0])
                 else:
                     want = g.pagerank(0.85, 10, 1)
                     ok = bool(np.max(np.abs(got - want) / want) < 1e-6)

@@ -87,6 +87,34 @@ def test_bfs_source_not_in_graph_and_isolated():
     frag.close()
 
 
+@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("ring", [0, 5, 16])
+def test_bfs_high_diameter_spills_level_ring(fuse, ring):
+    """A 1000-vertex path with side branches: depth far beyond a tiny level-bitmap
+    ring (cfg.reserved[3]) => the finished levels are spilled to the int32 depth
+    array and the query resumes; like the reference's depth array (bfs.h:31) the
+    depth is unbounded."""
+    n = 1000
+    src = np.arange(0, n - 1, dtype=np.int64)
+    dst = src + 1
+    extra_s = np.array([10, 10, 500, 998, 3], dtype=np.int64)
+    extra_d = np.array([700, 11, 502, 0, 3], dtype=np.int64)     # chords, a multi-edge and a self loop
+    s_all = np.concatenate([src, extra_s])
+    d_all = np.concatenate([dst, extra_d])
+    g = pyoracle.Graph(n, s_all, d_all, None)
+    frag = pkg().Fragment.from_edges(n, s_all, d_all)
+    for source in (0, 640):
+        app = app_available("bfs", frag, source_oid=source, fuse_supersteps=fuse, reserved={3: ring})
+        app.query()
+        want, _ = g.bfs(source)
+        assert want.max() > 100
+        assert np.array_equal(app.result(), want)
+        app.query()                      # state (ring + spill array) resets between queries
+        assert np.array_equal(app.result(), want)
+        app.close()
+    frag.close()
+
+
 # ------------------------------------------------------------------ SSSP ----
 def _sssp_render(oids, dist):
     big = np.finfo(np.float64).max
