@@ -151,8 +151,9 @@ def run_gpu(args):
         cfg["direction_opt"] = 0 if args.push_only else 1
         cfg["fuse_supersteps"] = 0 if args.no_fuse else 1
         if args.bfs_beta:
-            import ctypes
-            cfg["reserved"] = (ctypes.c_int * 8)(0, 0, args.bfs_beta, 0, 0, 0, 0, 0)
+            cfg.setdefault("reserved", {})[2] = args.bfs_beta
+    if args.no_hub_order:
+        cfg.setdefault("reserved", {})[1] = 1
     if args.app in ("pagerank", "cdlp"):
         cfg["max_round"] = 10
     if args.app == "pagerank" and args.pr_pull:
@@ -355,6 +356,7 @@ def main():
     ap.add_argument("--push-only", action="store_true")
     ap.add_argument("--cpu-scale", type=int, default=22, help="largest scale the CPU arm runs (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hub-order", action="store_true", help="disable the hub-first shadow CSR (BFS)")
     ap.add_argument("--bfs-beta", type=int, default=0, help="BFS pull->push threshold divisor (0 = library default)")
     ap.add_argument("--pr-pull", action="store_true", help="PageRank: deterministic pull step instead of atomicAdd push")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per superstep (profiling) instead of the fused query kernel")

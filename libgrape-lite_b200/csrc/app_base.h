@@ -80,7 +80,7 @@ namespace gl {
 int build_hub_order(cudaStream_t s, const uint64_t* rp, uint32_t n, uint32_t** perm_out, uint32_t** order_out);
 int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, uint64_t m, uint32_t n,
                        const uint32_t* order, const uint32_t* perm, uint64_t** rp_out, uint32_t** col_out,
-                       const void* w4 = nullptr, void** w4_out = nullptr);
+                       const void* w4 = nullptr, void** w4_out = nullptr, bool sort_rows = true);
 gl_app* make_bfs();
 gl_app* make_sssp_f32();
 gl_app* make_sssp_f64();

@@ -121,13 +121,10 @@ struct SsspApply {
   }
 };
 
-// perm != null: dist is indexed by the hub-first rank of a vertex
 template <typename T>
-__global__ void k_dist_to_f64(const T* d, uint32_t n, T inf, const uint32_t* perm, double* out) {
+__global__ void k_dist_to_f64(const T* d, uint32_t n, T inf, double* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const T v = d[perm ? perm[i] : i];
-  out[i] = v == inf ? DBL_MAX : (double) v;
+  if (i < n) out[i] = d[i] == inf ? DBL_MAX : (double) d[i];
 }
 
 template <typename T>
@@ -139,11 +136,6 @@ struct SsspApp : gl_app {
   uint32_t tvnum = 0;
   T init_prio = 0, prio = 0;
   uint64_t far_total = 0;
-  // hub-first relabelled shadow CSR with its weights (one fragment, 4-byte
-  // edge data) — see hub_order.cu; dist[] is indexed by rank
-  uint32_t *perm = nullptr, *order = nullptr, *col_p = nullptr;
-  uint64_t* rp_p = nullptr;
-  void* w_p = nullptr;
   static T inf() { return sizeof(T) == 4 ? (T) FLT_MAX : (T) DBL_MAX; }
 
   ~SsspApp() override {
@@ -153,11 +145,6 @@ struct SsspApp : gl_app {
     cudaFree(far);
     cudaFree(remote);
     cudaFree(out64);
-    cudaFree(perm);
-    cudaFree(order);
-    cudaFree(col_p);
-    cudaFree(rp_p);
-    cudaFree(w_p);
   }
   size_t ResultElemBytes() const override { return sizeof(double); }
 
@@ -192,11 +179,6 @@ struct SsspApp : gl_app {
       p = 32.0 * (wsum / m) / (m / iv);
     }
     init_prio = (T) p;
-    if (fv.fnum == 1 && fv.ivnum > 0 && fv.edata_bytes == 4 && fv.oe_w && cfg.reserved[1] == 0) {
-      GL_TRY(build_hub_order(eng.stream, fv.oe_rp, fv.ivnum, &perm, &order));
-      GL_TRY(build_permuted_csr(eng.stream, fv.oe_rp, fv.oe_col, frag->oe.entries, fv.ivnum, order, perm,
-                                &rp_p, &col_p, fv.oe_w, &w_p));
-    }
     return mm.Init(comm, fv, sizeof(ItemDist<T>));
   }
 
@@ -214,10 +196,8 @@ struct SsspApp : gl_app {
 
   int PEval() override {
     uint32_t src;
-    if (gl_frag_oid2lid(frag, cfg.source_oid, &src) == GL_OK) {
-      if (perm) GL_CUDA(cudaMemcpy(&src, perm + src, 4, cudaMemcpyDeviceToHost));
+    if (gl_frag_oid2lid(frag, cfg.source_oid, &src) == GL_OK)
       GL_LAUNCH(k_sssp_seed<T>, 1, 32, eng.stream, src, dist, in_q);
-    }
     mm.ForceContinue();
     return GL_OK;
   }
@@ -226,7 +206,6 @@ struct SsspApp : gl_app {
   int scan(cudaStream_t) {
     OpSssp<T, WT> op{dist, near, far, remote, fv.ivnum, prio};
     EdgeRange er{fv.oe_rp, fv.oe_col, fv.oe_w};
-    if (rp_p) er = EdgeRange{rp_p, col_p, w_p};
     return run_frontier_scan(eng, in_q, fv.ivnum, er, op);
   }
 
@@ -267,7 +246,7 @@ struct SsspApp : gl_app {
 
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
-    GL_LAUNCH(k_dist_to_f64<T>, (fv.ivnum + 255) / 256, 256, eng.stream, dist, fv.ivnum, inf(), perm, out64);
+    GL_LAUNCH(k_dist_to_f64<T>, (fv.ivnum + 255) / 256, 256, eng.stream, dist, fv.ivnum, inf(), out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(double) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
     GL_CUDA(cudaStreamSynchronize(eng.stream));
     return GL_OK;

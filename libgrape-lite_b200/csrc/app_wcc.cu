@@ -18,6 +18,9 @@
 namespace gl {
 namespace {
 
+// (A hub-first relabelled shadow CSR like the BFS one was measured here and
+// for SSSP: with DENSE frontiers it concentrates every heavy row in the first
+// tiles, and round 1 went from 4.9 ms to 36 ms on R-MAT-24 — not used.)
 struct OpWcc {
   using Meta = uint32_t;
   using W = float;
@@ -62,13 +65,11 @@ struct OpWccPull {
   }
 };
 
-// order != null: labels are stored at the hub-first rank of a vertex
-// (hub_order.cu) but keep their VALUE = gid of the original vertex
 __global__ void k_wcc_init(uint32_t* label, uint32_t ivnum, uint32_t ovnum,
                            const uint32_t* ovgid, uint32_t fid, int fid_offset,
-                           uint32_t* in_q, uint32_t words, const uint32_t* order) {
+                           uint32_t* in_q, uint32_t words) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < ivnum) label[i] = (fid << fid_offset) | (order ? order[i] : i);  // Vertex2Gid, inner
+  if (i < ivnum) label[i] = (fid << fid_offset) | i;       // Vertex2Gid, inner
   else if (i < ivnum + ovnum) label[i] = ovgid[i - ivnum];  // outer
   if (i < words) {
     // all inner vertices active
@@ -99,10 +100,10 @@ struct WccApply {
 __global__ void k_wcc_out(const uint32_t* label, uint32_t n, int fid_offset,
                           uint32_t id_mask, uint64_t chunk, uint32_t fnum,
                           const int64_t* inner_oids, int64_t oid_base,
-                          const uint32_t* perm, int64_t* out) {
+                          int64_t* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t g = label[perm ? perm[i] : i];
+  uint32_t g = label[i];
   uint32_t f = g >> fid_offset, l = g & id_mask;
   if (fnum == 1) {
     out[i] = inner_oids ? inner_oids[l] : oid_base + (int64_t) l;
@@ -119,11 +120,6 @@ struct WccApp : gl_app {
   size_t words = 0;
   uint32_t tvnum = 0;
   uint64_t active_estimate = 0;   // vertices active in the coming round
-  // hub-first relabelled shadow CSR (one fragment, symmetric adjacency): the
-  // label words of the high-degree vertices — the targets of most atomicMin
-  // traffic — become one contiguous, cache-resident prefix
-  uint32_t *perm = nullptr, *order = nullptr, *col_p = nullptr;
-  uint64_t* rp_p = nullptr;
 
   ~WccApp() override {
     cudaFree(label);
@@ -131,10 +127,6 @@ struct WccApp : gl_app {
     cudaFree(out_local);
     cudaFree(remote);
     cudaFree(out64);
-    cudaFree(perm);
-    cudaFree(order);
-    cudaFree(col_p);
-    cudaFree(rp_p);
   }
   size_t ResultElemBytes() const override { return sizeof(int64_t); }
 
@@ -146,11 +138,6 @@ struct WccApp : gl_app {
     GL_CUDA(cudaMalloc(&out_local, sizeof(uint32_t) * words));
     GL_CUDA(cudaMalloc(&remote, sizeof(uint32_t) * words));
     GL_CUDA(cudaMalloc(&out64, sizeof(int64_t) * std::max<uint32_t>(fv.ivnum, 1)));
-    if (fv.fnum == 1 && fv.ivnum > 0 && (!fv.directed || frag->ie_alias_oe) && cfg.reserved[1] == 0) {
-      GL_TRY(build_hub_order(eng.stream, fv.oe_rp, fv.ivnum, &perm, &order));
-      GL_TRY(build_permuted_csr(eng.stream, fv.oe_rp, fv.oe_col, frag->oe.entries, fv.ivnum, order, perm,
-                                &rp_p, &col_p));
-    }
     return mm.Init(comm, fv, sizeof(ItemU32U32));
   }
 
@@ -164,7 +151,7 @@ struct WccApp : gl_app {
   int PEval() override {
     uint32_t n = (uint32_t) std::max<size_t>(tvnum, words);
     GL_LAUNCH(k_wcc_init, (n + 255) / 256, 256, eng.stream, label, fv.ivnum, fv.ovnum,
-              fv.ovgid, fv.fid, fv.fid_offset, in_q, (uint32_t) words, order);
+              fv.ovgid, fv.fid, fv.fid_offset, in_q, (uint32_t) words);
     active_estimate = fv.ivnum;
     mm.ForceContinue();
     return GL_OK;
@@ -180,11 +167,11 @@ struct WccApp : gl_app {
       GL_TRY(eng.reset_ctrl());
     }
     OpWcc op{label, out_local, remote, fv.ivnum};
-    EdgeRange er{rp_p ? rp_p : fv.oe_rp, col_p ? col_p : fv.oe_col, nullptr};
+    EdgeRange er{fv.oe_rp, fv.oe_col, nullptr};
     // cfg.reserved[0] = 1 selects the pull sweep for dense rounds (measured
     // slower than the push scan on R-MAT-24: 8.5 ms vs 4.9 ms per round, so
     // it is off by default)
-    const bool dense = cfg.reserved[0] == 1 && !rp_p && fv.fnum == 1 && !fv.directed && frag->oe_ntiles > 0 &&
+    const bool dense = cfg.reserved[0] == 1 && fv.fnum == 1 && !fv.directed && frag->oe_ntiles > 0 &&
                        active_estimate > (uint64_t) fv.ivnum / 8;
     if (dense) {
       static thread_local int gd = 0;
@@ -223,7 +210,7 @@ struct WccApp : gl_app {
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
     GL_LAUNCH(k_wcc_out, (fv.ivnum + 255) / 256, 256, eng.stream, label, fv.ivnum, fv.fid_offset,
-              fv.id_mask, frag->part_chunk, fv.fnum, fv.inner_oids, fv.oid_base, perm, out64);
+              fv.id_mask, frag->part_chunk, fv.fnum, fv.inner_oids, fv.oid_base, out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(int64_t) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
     GL_CUDA(cudaStreamSynchronize(eng.stream));
     return GL_OK;

@@ -80,7 +80,7 @@ int build_hub_order(cudaStream_t s, const uint64_t* rp, uint32_t n, uint32_t** p
 // rows reordered by `order`, neighbours relabelled by `perm`
 int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, uint64_t m, uint32_t n,
                        const uint32_t* order, const uint32_t* perm, uint64_t** rp_out, uint32_t** col_out,
-                       const void* w4, void** w4_out) {
+                       const void* w4, void** w4_out, bool sort_rows) {
   uint64_t *deg = nullptr, *rp_p = nullptr;
   GL_CUDA(cudaMalloc(&deg, 8ull * ((size_t) n + 1)));
   GL_CUDA(cudaMalloc(&rp_p, 8ull * ((size_t) n + 1)));
@@ -98,7 +98,7 @@ int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, 
   // rows sorted by the new ids = by descending degree of the neighbour: the
   // most promising parents come first in a pull scan, and the entries of a
   // row that fall into the same bitmap word are adjacent
-  if (n && m) {
+  if (n && m && sort_rows) {
     uint32_t* sorted = nullptr;
     GL_CUDA(cudaMalloc(&sorted, 4ull * (m + 16)));
     size_t sb = 0;
