@@ -93,7 +93,8 @@ k_bfs_hub_nbr(const uint64_t* __restrict__ rp, const uint64_t* __restrict__ row_
     unsigned long long best = 0;
     for (uint64_t p = b + lane_id(); p < e; p += 32) {
       uint32_t u = col[p];
-      unsigned long long dg = rp[u + 1] - rp[u];
+      // outer copies have no local row: rank them below every inner neighbour
+      unsigned long long dg = u < ivnum ? rp[u + 1] - rp[u] + 1 : 1;
       if (dg > 0xFFFFFFFFull) dg = 0xFFFFFFFFull;
       uint64_t off = p - b;
       if (off > 0xFFFFFFFEull) off = 0xFFFFFFFEull;
@@ -334,6 +335,16 @@ struct BfsFusedCtl {
   uint32_t r_phase, r_pad;   // r_phase = ~0: derive from the seed
   unsigned long long p_nf, p_mf, p_visited_edges, p_visited_cnt;   // parked state (-> r_* by k_bfs_resume_prep)
   uint32_t p_phase, p_pad;
+  // multi-fragment fused kernel: result of the last in-kernel collective and
+  // how much of the communicator's sequence space the launch consumed
+  long long xres[4];
+  unsigned long long x_last_tag;
+  uint32_t x_msg_rounds, x_mirror_syncs;
+  unsigned long long x_items;   // items this GPU sent
+  unsigned long long ph[32][6];
+  unsigned long long xw[32][2];  // GL_TRACE: per level: peer wait / first grid.sync of its last xsync
+  unsigned long long xt[8];      // GL_TRACE: timestamps inside the most recent xsync (block 0, thread 0)   // GL_TRACE: phase timestamps of the first 32 levels (thread 0)
+  uint32_t x_error, x_pad;   // 1 = a peer did not show up in time, 2 = landing slot overflow
   BfsLevelStat stat[kMaxFusedStats];
 };
 
@@ -389,6 +400,10 @@ __global__ void k_bfs_seed_fused(uint32_t src, int has_src, uint32_t* lv0,
   ctl->r_visited_edges = deg;
   ctl->r_visited_cnt = has_src ? 1 : 0;
   ctl->r_phase = 0xFFFFFFFFu;
+  ctl->x_error = 0;
+  ctl->x_items = 0;
+  ctl->x_msg_rounds = 0;
+  ctl->x_mirror_syncs = 0;
   ctl->t_begin = global_ns();
 }
 
@@ -515,9 +530,383 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedAr
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Fused whole-query BFS over SEVERAL fragments: one cooperative launch per GPU
+// runs every level; the GPUs meet in device-side collectives over the NVLink-
+// mapped landing areas (comm.h) — no host round trip, no kernel launch and no
+// NCCL call between levels.
+//   push level: scan | grid.sync | hub scan | grid.sync | pack outer hits into
+//               the owners' landing slots | xsync (publishes item counts, sums
+//               the frontier statistics) | apply received items
+//   pull level: owners pack their frontier bits into the holders' mirror slots
+//               | xsync | holders OR them into their outer copies | pull |
+//               xsync (statistics)
+// Every decision is derived from the all-reduced statistics, so all GPUs take
+// the same branches and issue the same sequence of collectives.
+// ---------------------------------------------------------------------------
 struct BfsPayload {
   GL_DEV ItemU32 operator()(uint32_t, uint32_t lid) const { return ItemU32{lid}; }
 };
+
+struct XComm {
+  uint32_t fid, fnum;
+  int fid_offset;
+  uint32_t id_mask;
+  uint32_t capacity;                       // items per landing slot
+  PeerSlot* const* slot_at_peer[2];        // [tag parity][fnum]: my slot in peer p's header
+  const PeerSlot* local_slots;             // my header, parity 0 (parity 1 at + GL_MAX_FNUM)
+  unsigned long long tag0;                 // first sequence number this launch may use
+  char* const* send_slot[2];               // [msg parity][fnum]
+  const char* const* recv_slot[2];
+  uint32_t* const* peer_count[2];          // my count cell in peer p's header
+  const uint32_t* local_counts;            // my header counts[2][GL_MAX_FNUM]
+  uint32_t* send_count;                    // [fnum] local reservation counters
+  uint32_t msg_round0, mirror_seq0;
+  const uint32_t* mirror_lids;
+  const uint64_t* mirror_off;
+  MirrorBitsPlan plan;                     // word-parallel pack (plan.mask == null: lid-list pack)
+  char* const* msend[2];
+  const char* const* mrecv[2];
+  const uint32_t* ghost_range;
+};
+
+struct XSmem {
+  long long v[4][GL_MAX_FNUM];
+  unsigned int total;
+};
+
+constexpr unsigned long long kXsyncTimeoutNs = 5000000000ull;
+
+// Grid-wide + cross-GPU barrier and sum.  C != null: contribution =
+// (next_count, items published, next_edges) of that control block; otherwise
+// (e0, e1, 0).  publish_par >= 0: block 0 first publishes this round's item
+// counts into the peers' headers.  Returns false when the launch must abort.
+GL_DEV unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+GL_DEV void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// In-kernel collectives do not use PeerSlot::tag: each of the three 8-byte
+// payload words carries a 16-bit stamp (0x4000 | tag mod 2^14) above a 48-bit
+// value, so a contribution is three independent atomic 8-byte peer stores with
+// no fence between payload and flag.  (The stamp can never equal the top bits
+// of a raw value written by the host-launched k_peer_allreduce: 0 or 0xFFFF.)
+GL_DEV unsigned long long x_stamp(unsigned long long tag) { return (0x4000ull | (tag & 0x3FFFull)) << 48; }
+
+GL_DEV bool xsync(cg::grid_group& grid, const XComm& x, XSmem& xs, unsigned long long tag,
+                  int publish_par, const ScanCtrl* C, long long e0, long long e1,
+                  BfsFusedCtl* ctl, long long out[3], bool peer_stores = true) {
+  if (__syncthreads_or(peer_stores ? 1 : 0)) {
+    // the CTA's peer stores (items, mirror words) must be visible system-wide
+    // before the stamp: bar.sync makes them happen-before thread 0's fence, which
+    // is cumulative (one fence.sys per CTA instead of one per thread: a
+    // fence.sys from every thread cost ~15 us per collective)
+    // (~7 us: only CTAs that actually stored to a peer since the last collective pay it)
+    if (threadIdx.x == 0) __threadfence_system();
+  }
+  const bool tr = blockIdx.x == 0 && threadIdx.x == 0;
+  if (tr) ctl->xt[0] = global_ns();
+  grid.sync();
+  if (tr) ctl->xt[1] = global_ns();
+  if (blockIdx.x == 0) {
+    const uint32_t p = threadIdx.x;
+    if (p == 0) xs.total = 0;
+    __syncthreads();
+    if (publish_par >= 0 && p < x.fnum) {
+      const uint32_t c = *(volatile uint32_t*) (x.send_count + p);
+      if (p != x.fid) {
+        *x.peer_count[publish_par][p] = c;   // NVLink peer store (ordered before the stamp by the fence below)
+        atomicAdd(&xs.total, c);
+        if (c > x.capacity) ctl->x_error = 2;
+      }
+      x.send_count[p] = 0;
+    }
+    __syncthreads();
+    if (p < x.fnum) {
+      unsigned long long i0 = (unsigned long long) e0, i1 = (unsigned long long) e1, i2 = 0;
+      if (C) {
+        const volatile ScanCtrl* VC = C;
+        i0 = VC->next_count;
+        i1 = xs.total;
+        i2 = VC->next_edges;
+      }
+      const unsigned long long st = x_stamp(tag), vm = 0xFFFFFFFFFFFFull;
+      PeerSlot* dst = x.slot_at_peer[tag & 1][p];
+      if (publish_par >= 0) __threadfence_system();   // my count cell before my stamp
+      st_relaxed_sys_u64((unsigned long long*) &dst->i0, st | (i0 & vm));
+      st_relaxed_sys_u64((unsigned long long*) &dst->i1, st | (i1 & vm));
+      st_relaxed_sys_u64((unsigned long long*) &dst->i2, st | (i2 & vm));
+      const PeerSlot* src = x.local_slots + (tag & 1) * GL_MAX_FNUM + p;
+      const unsigned long long t0 = global_ns();
+      if (tr) ctl->xt[2] = t0;
+      bool ok = true;
+      unsigned long long r0, r1, r2;
+      for (;;) {
+        r0 = ld_acquire_sys_u64((const unsigned long long*) &src->i0);
+        r1 = ld_acquire_sys_u64((const unsigned long long*) &src->i1);
+        r2 = ld_acquire_sys_u64((const unsigned long long*) &src->i2);
+        if ((r0 & ~vm) == st && (r1 & ~vm) == st && (r2 & ~vm) == st) break;
+        __nanosleep(20);
+        if (global_ns() - t0 > kXsyncTimeoutNs) {
+          ok = false;
+          break;
+        }
+      }
+      if (!ok) ctl->x_error = 1;
+      if (tr) ctl->xt[3] = global_ns();
+      xs.v[0][p] = (long long) (r0 & vm);
+      xs.v[1][p] = (long long) (r1 & vm);
+      xs.v[2][p] = (long long) (r2 & vm);
+    }
+    __syncthreads();
+    if (p == 0) {
+      long long a = 0, b = 0, c = 0;
+      for (uint32_t q = 0; q < x.fnum; ++q) {
+        a += xs.v[0][q];
+        b += xs.v[1][q];
+        c += xs.v[2][q];
+      }
+      ctl->xres[0] = a;
+      ctl->xres[1] = b;
+      ctl->xres[2] = c;
+      ctl->x_last_tag = tag;
+      if (publish_par >= 0) ctl->x_items += xs.total;
+      __threadfence();
+    }
+  }
+  grid.sync();
+  if (tr) ctl->xt[4] = global_ns();
+  const volatile BfsFusedCtl* V = ctl;
+  out[0] = V->xres[0];
+  out[1] = V->xres[1];
+  out[2] = V->xres[2];
+  return V->x_error == 0;
+}
+
+// owner -> holders: the bits of `bitmap` at my mirrored inner vertices, then
+// (after the barrier) OR the words received from every owner into my outer copies
+GL_DEV bool mirror_pack(const XComm& x, uint32_t par, const uint32_t* bitmap) {
+  const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+  const uint64_t gtid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (x.plan.mask) return mirror_pack_bits_phase(x.plan, bitmap, x.msend[par], gtid, nthreads);
+  for (uint32_t g = 0; g < x.fnum; ++g) {
+    const uint64_t b = x.mirror_off[g], n = x.mirror_off[g + 1] - b;
+    if (!n) continue;
+    uint32_t* out = (uint32_t*) x.msend[par][g];
+    const uint64_t npad = (n + 31) & ~31ull;
+    for (uint64_t k = gtid; k < npad; k += nthreads) {
+      bool bit = false;
+      if (k < n) bit = bit_test(bitmap, x.mirror_lids[b + k]);
+      const uint32_t w = __ballot_sync(0xffffffffu, bit);
+      if (lane_id() == 0) out[k >> 5] = w;
+    }
+  }
+  return true;
+}
+GL_DEV void mirror_unpack(const XComm& x, uint32_t par, uint32_t* bitmap) {
+  const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+  const uint64_t gtid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t f = 0; f < x.fnum; ++f) {
+    const uint32_t base = x.ghost_range[f], n = x.ghost_range[f + 1] - base;
+    if (!n || f == x.fid) continue;
+    const uint32_t nw = (n + 31) >> 5;
+    const uint32_t* in = (const uint32_t*) x.mrecv[par][f];
+    for (uint64_t j = gtid; j < nw; j += nthreads) {
+      const uint32_t w = __ldcg(in + j);   // written by the peer: bypass L1
+      if (!w) continue;
+      const uint32_t pos = base + ((uint32_t) j << 5), sh = pos & 31;
+      atomicOr(bitmap + (pos >> 5), w << sh);
+      if (sh) atomicOr(bitmap + (pos >> 5) + 1, w >> (32 - sh));
+    }
+  }
+}
+GL_DEV bool mirror_sync_bits(cg::grid_group& grid, const XComm& x, XSmem& xs, unsigned long long tag,
+                             uint32_t par, uint32_t* bitmap, BfsFusedCtl* ctl) {
+  const bool wrote = mirror_pack(x, par, bitmap);
+  long long dummy[3];
+  if (!xsync(grid, x, xs, tag, -1, nullptr, 0, 0, ctl, dummy, wrote)) return false;
+  mirror_unpack(x, par, bitmap);
+  grid.sync();
+  return true;
+}
+
+struct BfsMultiArgs {
+  BfsFusedArgs f;
+  uint32_t* remote;
+  uint32_t ovnum;
+  const uint32_t* ovgid;
+  unsigned long long g_m_total, g_vnum;
+  XComm x;
+};
+
+__global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsMultiArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ union {
+    ScanSmem<uint32_t> scan;
+    PullSmem pull;
+    XSmem xs;
+    PackSmem pack;
+  } sm;
+  __shared__ uint32_t s_item;
+  const BfsFusedArgs& a = A.f;
+  const XComm& x = A.x;
+  BfsFusedCtl* ctl = a.ctl;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+  unsigned long long tag = x.tag0;
+  uint32_t msg_round = x.msg_round0, mseq = x.mirror_seq0;
+  unsigned long long n_f, m_f, visited_edges;
+  uint32_t phase = ctl->r_phase;
+  bool premirrored = false;
+  long long S[3];
+  if (gtid == 0) ctl->x_last_tag = x.tag0 - 1;   // (same thread later records every collective)
+  if (phase == 0xFFFFFFFFu) {
+    // first launch of the query: the source's owner contributes (1, deg)
+    if (!xsync(grid, x, sm.xs, tag++, -1, nullptr, (long long) ctl->r_nf, (long long) ctl->r_mf, ctl, S)) return;
+    n_f = (unsigned long long) S[0];
+    m_f = (unsigned long long) S[1];
+    visited_edges = m_f;
+    phase = 0;
+  } else {
+    n_f = ctl->r_nf;
+    m_f = ctl->r_mf;
+    visited_edges = ctl->r_visited_edges;
+  }
+  for (uint32_t depth = 0; n_f != 0; ++depth) {
+    if (depth + 1 >= a.max_lv) {
+      if (gtid == 0) {
+        ctl->overflow = 1;
+        ctl->p_nf = n_f;
+        ctl->p_mf = m_f;
+        ctl->p_visited_edges = visited_edges;
+        ctl->p_visited_cnt = 0;
+        ctl->p_phase = phase;
+      }
+      break;
+    }
+    // direction on WHOLE-GRAPH statistics (identical on every GPU)
+    const unsigned long long m_u = A.g_m_total > visited_edges ? A.g_m_total - visited_edges : 0;
+    uint32_t nphase = 0;
+    if (!a.direction_opt) nphase = 0;
+    else if (phase == 0) nphase = (m_f > m_u / 14) ? 1u : 0u;
+    else if (phase == 1) nphase = (n_f >= A.g_vnum / a.beta) ? 1u : 2u;
+    else nphase = 2;
+    ScanCtrl* C = &ctl->c[depth % 3];
+    uint32_t* cur = a.lv + (size_t) depth * a.words;
+    uint32_t* nxt = a.lv + (size_t) (depth + 1) * a.words;
+    ScanAcc acc;
+    const uint32_t tl = a.depth_base + depth;
+#define GL_MARK(k) do { if (gtid == 0 && tl < 32) ctl->ph[tl][k] = global_ns(); } while (0)
+    GL_MARK(0);
+    if (nphase != 1) {
+      premirrored = false;   // (a speculative shipment of this frontier stays unused)
+      if (phase == 1) {
+        // leaving the pull phase: outer copies learn which vertices their
+        // owners visited meanwhile, so they are not reported again
+        ++mseq;
+        if (!mirror_sync_bits(grid, x, sm.xs, tag++, mseq & 1, a.vis, ctl)) return;
+      }
+      OpBfsPush op{a.vis, nxt, A.remote, a.er.rp, a.pa.ivnum};
+      GL_MARK(1);
+      frontier_scan_phase<OpBfsPush>(sm.scan, cur, a.pa.ivnum, a.er, op, C, a.hubs, a.hub_cap, a.hub_deg, acc);
+      grid.sync();
+      hub_scan_phase<OpBfsPush>(&s_item, a.er, op, C, a.hubs, a.hub_cap, acc);
+      flush_acc(acc, C);
+      grid.sync();
+      GL_MARK(2);
+      // report newly reached outer copies to their owners (k_pack_outer)
+      const uint32_t par = msg_round & 1;
+      bool wrote_items = false;
+      {
+        MsgView mv;
+        mv.fid = x.fid;
+        mv.fnum = x.fnum;
+        mv.fid_offset = x.fid_offset;
+        mv.id_mask = x.id_mask;
+        mv.item_bytes = 4;
+        mv.capacity = x.capacity;
+        mv.send_slot = x.send_slot[par];
+        mv.send_count = x.send_count;
+        mv.recv_slot = nullptr;
+        mv.recv_count = nullptr;
+        wrote_items = pack_outer_phase<ItemU32, BfsPayload>(sm.pack, A.remote, a.pa.ivnum, A.ovnum, A.ovgid, mv,
+                                                            BfsPayload(), true);
+      }
+      GL_MARK(3);
+      if (!xsync(grid, x, sm.xs, tag++, (int) par, C, 0, 0, ctl, S, wrote_items)) return;
+      GL_MARK(4);
+      if (S[1] > 0) {
+        // apply what the other fragments found (ParallelProcess, bfs.h:158-166)
+        for (uint32_t src = 0; src < x.fnum; ++src) {
+          if (src == x.fid) continue;
+          const uint32_t n = __ldcg(x.local_counts + par * GL_MAX_FNUM + src);
+          const uint32_t* items = (const uint32_t*) x.recv_slot[par][src];
+          for (uint64_t i = gtid; i < n; i += nthreads) {
+            const uint32_t v = __ldcg(items + i);
+            if (bit_set_atomic(a.vis, v)) bit_set_atomic(nxt, v);
+          }
+        }
+        grid.sync();
+      }
+      GL_MARK(5);
+      ++msg_round;
+    } else {
+      if (!premirrored) {
+        ++mseq;
+        if (!mirror_sync_bits(grid, x, sm.xs, tag++, mseq & 1, cur, ctl)) return;
+      } else {
+        // the previous pull level already shipped this frontier with its statistics
+        mirror_unpack(x, mseq & 1, cur);
+        grid.sync();
+      }
+      GL_MARK(1);
+      bfs_pull_phase(sm.pull, a.pa, cur, a.vis, nxt, C, acc);
+      flush_acc(acc, C);
+      grid.sync();
+      GL_MARK(2);
+      // A pull level is usually followed by another one: ship the new frontier's
+      // bits to the holders NOW, so the statistics collective is also the mirror
+      // barrier of the next level (one cross-GPU exchange per pull level, not two)
+      ++mseq;
+      const bool wrote = mirror_pack(x, mseq & 1, nxt);
+      if (!xsync(grid, x, sm.xs, tag++, -1, C, 0, 0, ctl, S, wrote)) return;
+      premirrored = true;
+      GL_MARK(4);
+    }
+#undef GL_MARK
+    phase = nphase;
+    if (gtid == 0) {
+      if (tl < 32) {
+        ctl->xw[tl][0] = ctl->xt[3] - ctl->xt[2];
+        ctl->xw[tl][1] = ctl->xt[1] - ctl->xt[0];
+      }
+      const volatile ScanCtrl* VC = C;
+      const uint32_t adepth = a.depth_base + depth;
+      if (adepth < (uint32_t) kMaxFusedStats) {
+        BfsLevelStat ls;
+        ls.t_ns = global_ns();
+        ls.scanned = VC->scanned;
+        ls.frontier = (uint32_t) (n_f > 0xFFFFFFFFull ? 0xFFFFFFFFull : n_f);
+        ls.mode = phase == 1 ? 1u : 0u;
+        ctl->stat[adepth] = ls;
+      }
+      ctl->levels = adepth + 1;
+      ctl->touched += VC->touched;
+      ctl->c[(depth + 2) % 3] = ScanCtrl();
+      ctl->x_msg_rounds = msg_round - x.msg_round0;
+      ctl->x_mirror_syncs = mseq - x.mirror_seq0;
+    }
+    n_f = (unsigned long long) (S[0] + S[1]);
+    m_f = (unsigned long long) S[2];
+    visited_edges += m_f;
+  }
+}
+
 struct BfsApply {
   uint32_t* cur;
   uint32_t* vis;
@@ -666,6 +1055,10 @@ struct BfsApp : gl_app {
       GL_TRY(mm.PeerAllReduce(eng.stream, &a, &b, &c, 0));
       g_m_total = (uint64_t) a;
       g_vnum = (uint64_t) b;
+      // every GPU must spill its level ring at the same depth
+      long long lo = (long long) max_lv, dummy = 0;
+      GL_TRY(mm.PeerAllReduce(eng.stream, &lo, &dummy, &c, 1));
+      max_lv = (uint32_t) lo;
     }
     return GL_OK;
   }
@@ -715,7 +1108,9 @@ struct BfsApp : gl_app {
     return PullArgs{g_rp, row_end(), g_col, hub_nbr, fv.ivnum, g_nz};
   }
 
-  bool fused() const { return cfg.fuse_supersteps && fv.fnum == 1; }
+  bool fused() const {
+    return cfg.fuse_supersteps && (fv.fnum == 1 || (mm.use_peer_barrier && comm && comm->opened));
+  }
 
   // Fused path: the whole query is one cooperative launch (PEval seeds and
   // launches; no IncEval round is needed afterwards).
@@ -725,7 +1120,7 @@ struct BfsApp : gl_app {
     int has_src = has_src_;
     src = src_;   // already translated to the hub-first rank in Setup
     GL_LAUNCH(k_bfs_seed_fused, 1, 32, s, src, has_src, level_bm(0), vis, g_rp,
-              (unsigned long long) frag->oe.entries, d_ctl);
+              (unsigned long long) g_m_total, d_ctl);
     BfsFusedArgs a;
     a.pa = pull_args();
     a.er = EdgeRange{g_rp, g_col, nullptr};
@@ -740,18 +1135,84 @@ struct BfsApp : gl_app {
     a.hubs = eng.hubs;
     a.hub_cap = eng.hub_cap;
     a.hub_deg = eng.hub_deg;
-    if (!fused_grid) fused_grid = persistent_grid(k_bfs_fused, eng.sm_count);
+    const bool multi = fv.fnum > 1;
+    if (!fused_grid)
+      fused_grid = multi ? persistent_grid(k_bfs_fused_multi, eng.sm_count) : persistent_grid(k_bfs_fused, eng.sm_count);
+    BfsMultiArgs ma;
+    if (multi) {
+      ma.remote = remote;
+      ma.ovnum = fv.ovnum;
+      ma.ovgid = fv.ovgid;
+      ma.g_m_total = g_m_total;
+      ma.g_vnum = g_vnum;
+      XComm& x = ma.x;
+      x.fid = fv.fid;
+      x.fnum = fv.fnum;
+      x.fid_offset = fv.fid_offset;
+      x.id_mask = fv.id_mask;
+      x.capacity = (uint32_t) std::min<size_t>(comm->landing_bytes / sizeof(ItemU32), 0xFFFFFFFFu);
+      x.local_slots = (const PeerSlot*) (comm->local_base + GL_COMM_SLOT_OFF);
+      x.local_counts = (const uint32_t*) comm->local_base;
+      x.send_count = mm.d_send_count;
+      x.mirror_lids = mm.d_mirror_lids;
+      x.mirror_off = mm.d_mirror_off;
+      x.plan = mm.bits_plan();
+      if (!mm.mirror_sorted) x.plan.mask = nullptr;
+      x.ghost_range = mm.d_ghost_range;
+      for (int par = 0; par < 2; ++par) {
+        x.slot_at_peer[par] = mm.d_peer_slot[par];
+        x.send_slot[par] = mm.d_send_slot[par];
+        x.recv_slot[par] = mm.d_recv_slot[par];
+        x.peer_count[par] = mm.d_peer_count[par];
+        x.msend[par] = mm.d_msend[par];
+        x.mrecv[par] = mm.d_mrecv[par];
+      }
+    }
     for (;;) {
       a.depth_base = depth_base;
-      void* args[] = {&a};
-      GL_CUDA(cudaLaunchCooperativeKernel((void*) k_bfs_fused, dim3(fused_grid), dim3(kTB), args, 0, s));
+      if (multi) {
+        ma.f = a;
+        ma.x.tag0 = comm->seq_base + 1;
+        ma.x.msg_round0 = (uint32_t) mm.round;
+        ma.x.mirror_seq0 = (uint32_t) mm.mirror_seq;
+        void* args[] = {&ma};
+        GL_CUDA(cudaLaunchCooperativeKernel((void*) k_bfs_fused_multi, dim3(fused_grid), dim3(kTB), args, 0, s));
+      } else {
+        void* args[] = {&a};
+        GL_CUDA(cudaLaunchCooperativeKernel((void*) k_bfs_fused, dim3(fused_grid), dim3(kTB), args, 0, s));
+      }
       GL_COUNT_LAUNCH();
       GL_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BfsFusedCtl), cudaMemcpyDeviceToHost, s));
       GL_CUDA(cudaStreamSynchronize(s));
+      if (multi) {
+        comm->seq_base = h_ctl->x_last_tag;
+        mm.round += (int) h_ctl->x_msg_rounds;
+        mm.mirror_seq += h_ctl->x_mirror_syncs;
+        if (h_ctl->x_error) {
+          set_error(h_ctl->x_error == 2 ? "fused BFS: landing slot overflow"
+                                        : "fused BFS: a peer GPU did not reach the in-kernel barrier in time");
+          return GL_ERR_COMM;
+        }
+      }
       if (!h_ctl->overflow) break;
       // deeper than the ring: spill and resume (high-diameter graphs)
       GL_TRY(SpillRing());
       GL_LAUNCH(k_bfs_resume_prep, 1, 32, s, d_ctl);
+    }
+    if (multi) mm.bytes_sent += h_ctl->x_items * sizeof(ItemU32);
+    if (multi && trace_on()) {
+      for (uint32_t l = 0; l < h_ctl->levels && l < 32; ++l) {
+        const unsigned long long* t = h_ctl->ph[l];
+        char line[256];
+        int o = snprintf(line, sizeof(line), "[gl-trace] f%u level %2u mode %u:", fv.fid, l, h_ctl->stat[l].mode);
+        for (int k = 1; k < 6; ++k)
+          o += snprintf(line + o, sizeof(line) - o, " %7.1f", t[k] > t[0] ? (double) (t[k] - t[0]) * 1e-3 : -1.0);
+        snprintf(line + o, sizeof(line) - o, " us | peer-wait %.1f gs1 %.1f\n", h_ctl->xw[l][0] * 1e-3, h_ctl->xw[l][1] * 1e-3);
+        fputs(line, stderr);
+      }
+      fprintf(stderr, "[gl-trace] last xsync: gs1 %.1f  pre %.1f  wait %.1f  gs2 %.1f us\n",
+              (h_ctl->xt[1] - h_ctl->xt[0]) * 1e-3, (h_ctl->xt[2] - h_ctl->xt[1]) * 1e-3,
+              (h_ctl->xt[3] - h_ctl->xt[2]) * 1e-3, (h_ctl->xt[4] - h_ctl->xt[3]) * 1e-3);
     }
     used_lv = h_ctl->levels - depth_base + 1;
     q_touched += h_ctl->touched;

@@ -136,6 +136,57 @@ __global__ void k_mirror_pack_bits(const uint32_t* __restrict__ bitmap, const ui
     if ((threadIdx.x & 31) == 0) out[k >> 5] = w;
   }
 }
+
+// ---- word-parallel bit plan (MirrorBitsPlan) ---------------------------------
+__global__ void k_mirror_check_sorted(const uint32_t* __restrict__ lids, const uint64_t* __restrict__ off,
+                                      uint32_t fnum, uint32_t* bad) {
+  const uint32_t g = blockIdx.y;
+  const uint64_t b = off[g], n = off[g + 1] - b;
+  for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k + 1 < n; k += (uint64_t) gridDim.x * blockDim.x)
+    if (lids[b + k] >= lids[b + k + 1]) *bad = 1;
+  (void) fnum;
+}
+__global__ void k_mirror_mask(const uint32_t* __restrict__ lids, const uint64_t* __restrict__ off,
+                              uint32_t iv_words, uint32_t* mask) {
+  const uint32_t g = blockIdx.y;
+  const uint64_t b = off[g], n = off[g + 1] - b;
+  for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t) gridDim.x * blockDim.x) {
+    const uint32_t l = lids[b + k];
+    atomicOr(mask + (size_t) g * iv_words + (l >> 5), 1u << (l & 31));
+  }
+}
+// one CTA per holder: pref[w] = mirrored vertices before word w
+__global__ void __launch_bounds__(kTB) k_mirror_pref(const uint32_t* __restrict__ mask, uint32_t iv_words, uint32_t* pref) {
+  __shared__ uint32_t s_warp[kTB / 32 + 1];
+  const uint32_t g = blockIdx.x;
+  uint32_t run = 0;
+  for (uint32_t base = 0; base < iv_words; base += kTB) {
+    const uint32_t w = base + threadIdx.x;
+    const uint32_t c = w < iv_words ? __popc(mask[(size_t) g * iv_words + w]) : 0;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan(c, s_warp, &total);
+    if (w < iv_words) pref[(size_t) g * iv_words + w] = run + ex;
+    run += total;
+  }
+}
+// startw[woff[g] + j] = input word holding output bit 32 j of holder g
+__global__ void k_mirror_startw(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ pref,
+                                uint32_t iv_words, const uint64_t* __restrict__ woff, uint32_t* startw) {
+  const uint32_t g = blockIdx.y;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < iv_words; w += gridDim.x * blockDim.x) {
+    const uint32_t c = __popc(mask[(size_t) g * iv_words + w]);
+    if (!c) continue;
+    const uint32_t p0 = pref[(size_t) g * iv_words + w];
+    // output bits [p0, p0 + c) live in this word; those that are multiples of 32 start an output word
+    for (uint32_t j = (p0 + 31) >> 5; (j << 5) < p0 + c; ++j) startw[woff[g] + j] = w;
+  }
+}
+__global__ void __launch_bounds__(256) k_mirror_pack_bits2(MirrorBitsPlan P, const uint32_t* __restrict__ bitmap,
+                                                          char* const* msend) {
+  mirror_pack_bits_phase(P, bitmap, msend, (uint64_t) blockIdx.x * blockDim.x + threadIdx.x,
+                         (uint64_t) gridDim.x * blockDim.x);
+}
+
 // holder side: OR the received words into the ghost positions of my bitmap
 // (one thread per 32 outer copies; the ghost range of an owner is contiguous
 // but not word aligned, hence the two-part shifted OR)
@@ -279,13 +330,58 @@ int MessageManager::BuildMirrorPlan(cudaStream_t s, const gl_frag_view& fv) {
   GL_CUDA(cudaMemsetAsync(comm->local_base, 0, sizeof(uint32_t) * 2 * GL_MAX_FNUM, s));
   GL_TRY(PeerBarrier(s));
   mirror_seq = 0;
+  // word-parallel form for bit syncs (needs ascending lids per holder)
+  mirror_sorted = false;
+  if (mirror_total && fv.ivnum) {
+    uint32_t* d_bad = nullptr;
+    GL_CUDA(cudaMalloc(&d_bad, 4));
+    GL_CUDA(cudaMemsetAsync(d_bad, 0, 4, s));
+    dim3 grid(148 * 4, fnum);
+    k_mirror_check_sorted<<<grid, 256, 0, s>>>(d_mirror_lids, d_mirror_off, fnum, d_bad);
+    uint32_t bad = 1;
+    GL_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+    GL_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_bad);
+    if (!bad) {
+      iv_words = (uint32_t) ((fv.ivnum + 31) / 32);
+      std::vector<uint64_t> woff(fnum + 1, 0);
+      for (uint32_t g = 0; g < fnum; ++g) woff[g + 1] = woff[g] + (mirror_off[g + 1] - mirror_off[g] + 31) / 32;
+      mirror_out_words = woff[fnum];
+      GL_CUDA(cudaMalloc(&d_mirror_mask, sizeof(uint32_t) * (size_t) fnum * iv_words));
+      GL_CUDA(cudaMalloc(&d_mirror_pref, sizeof(uint32_t) * (size_t) fnum * iv_words));
+      GL_CUDA(cudaMalloc(&d_mirror_startw, sizeof(uint32_t) * std::max<uint64_t>(mirror_out_words, 1)));
+      GL_CUDA(cudaMalloc(&d_mirror_woff, sizeof(uint64_t) * (fnum + 1)));
+      GL_CUDA(cudaMemcpyAsync(d_mirror_woff, woff.data(), sizeof(uint64_t) * (fnum + 1), cudaMemcpyHostToDevice, s));
+      GL_CUDA(cudaMemsetAsync(d_mirror_mask, 0, sizeof(uint32_t) * (size_t) fnum * iv_words, s));
+      k_mirror_mask<<<grid, 256, 0, s>>>(d_mirror_lids, d_mirror_off, iv_words, d_mirror_mask);
+      k_mirror_pref<<<fnum, kTB, 0, s>>>(d_mirror_mask, iv_words, d_mirror_pref);
+      k_mirror_startw<<<grid, 256, 0, s>>>(d_mirror_mask, d_mirror_pref, iv_words, d_mirror_woff, d_mirror_startw);
+      GL_CUDA(cudaGetLastError());
+      GL_CUDA(cudaStreamSynchronize(s));
+      mirror_sorted = true;
+    }
+  }
   return GL_OK;
+}
+
+MirrorBitsPlan MessageManager::bits_plan() const {
+  MirrorBitsPlan P;
+  P.fnum = fnum;
+  P.iv_words = iv_words;
+  P.mask = d_mirror_mask;
+  P.pref = d_mirror_pref;
+  P.startw = d_mirror_startw;
+  P.woff = d_mirror_woff;
+  P.off = d_mirror_off;
+  return P;
 }
 
 int MessageManager::SyncBitsToGhosts(cudaStream_t s, uint32_t* bitmap) {
   if (fnum == 1) return GL_OK;
   const int par = (int) (++mirror_seq & 1);
-  if (mirror_total) {
+  if (mirror_total && mirror_sorted) {
+    GL_LAUNCH(k_mirror_pack_bits2, 148 * 8, 256, s, bits_plan(), bitmap, d_msend[par]);
+  } else if (mirror_total) {
     dim3 grid(148 * 8, fnum);
     GL_LAUNCH(k_mirror_pack_bits, grid, 256, s, bitmap, d_mirror_lids, d_mirror_off, d_msend[par]);
   }
@@ -396,6 +492,12 @@ void MessageManager::Destroy() {
   }
   if (d_mirror_lids) cudaFree(d_mirror_lids);
   if (d_mirror_off) cudaFree(d_mirror_off);
+  cudaFree(d_mirror_mask);
+  cudaFree(d_mirror_pref);
+  cudaFree(d_mirror_startw);
+  cudaFree(d_mirror_woff);
+  d_mirror_mask = d_mirror_pref = d_mirror_startw = nullptr;
+  d_mirror_woff = nullptr;
   if (d_scratch_result) cudaFree(d_scratch_result);
   d_scratch_result = nullptr;
   d_mirror_lids = nullptr;

@@ -30,7 +30,7 @@ def main():
         dist.all_gather_object(out, arr)
         return np.concatenate(out)
 
-    for wmode, apps in ((0, ["bfs", "bfs_push", "wcc", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp"])):
+    for wmode, apps in ((0, ["bfs", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp"])):
         n = 1 << scale
         frag = pkg.Fragment.rmat(scale, 16, seed=17, weight_mode=wmode, fid=rank, fnum=world)
         comm = gdist.make_comm(rank, world, frag.ivnum)
@@ -49,7 +49,10 @@ def main():
             kind = name
             if name.startswith("bfs"):
                 kind = "bfs"
-                cfg = dict(source_oid=source, direction_opt=0 if name == "bfs_push" else 1)
+                # default = whole query fused into one cooperative kernel per GPU;
+                # *_step = one superstep per round through the host loop
+                cfg = dict(source_oid=source, direction_opt=0 if "push" in name else 1,
+                           fuse_supersteps=0 if name.endswith("_step") else 1)
             elif name == "sssp":
                 cfg = dict(source_oid=source)
             elif name.startswith("pagerank"):
@@ -74,7 +77,7 @@ def main():
                 else:
                     want = g.pagerank(0.85, 10, 1)
                     ok = bool(np.max(np.abs(got - want) / want) < 1e-6)
-                print("[mgpu] %-9s fnum=%d scale=%d supersteps=%d msg_bytes=%d %s"
+                print("[mgpu] %-13s fnum=%d scale=%d supersteps=%d msg_bytes=%d %s"
                       % (name, world, scale, st.supersteps, st.msg_bytes_sent, "OK" if ok else "MISMATCH"), flush=True)
                 if not ok:
                     failures.append(name)
