@@ -176,38 +176,57 @@ GL_DEV bool mirror_pack_bits_phase(const MirrorBitsPlan& P, const uint32_t* __re
                                    char* const* msend, uint64_t gtid, uint64_t nthreads) {
   const uint64_t total = P.woff[P.fnum];
   const bool wrote = gtid < total;
-  for (uint64_t i = gtid; i < total; i += nthreads) {
-    uint32_t g = 0;
-    while (g + 1 < P.fnum && i >= P.woff[g + 1]) ++g;
-    const uint64_t j = i - P.woff[g];
-    const uint64_t nbits = P.off[g + 1] - P.off[g];
-    const uint32_t need = (uint32_t) ((nbits - 32 * j) < 32 ? (nbits - 32 * j) : 32);
-    const uint32_t* mask = P.mask + (size_t) g * P.iv_words;
-    const uint32_t* pref = P.pref + (size_t) g * P.iv_words;
-    uint32_t w = P.startw[i];
-    uint32_t skip = (uint32_t) (32 * j - pref[w]);
-    uint32_t out = 0, k = 0;
-    while (k < need) {
-      uint32_t sel = mask[w];
-      const uint32_t val = bitmap[w];
-      if (skip == 0 && sel == 0xFFFFFFFFu && k == 0 && need == 32) {   // dense fast path
-        out = val;
-        k = 32;
-        break;
-      }
-      while (skip && sel) {
-        sel &= sel - 1;
-        --skip;
-      }
-      while (sel && k < need) {
-        const uint32_t b = __ffs(sel) - 1;
-        out |= ((val >> b) & 1u) << k;
-        ++k;
-        sel &= sel - 1;
-      }
-      ++w;
+  constexpr int kB = 4;   // output words in flight per thread (the loads of a word form a dependent chain)
+  for (uint64_t i0 = gtid; i0 < total; i0 += (uint64_t) kB * nthreads) {
+    uint32_t w[kB], g[kB], need[kB], skip[kB], sel[kB], val[kB];
+    uint64_t j[kB];
+    bool ok[kB];
+#pragma unroll
+    for (int q = 0; q < kB; ++q) {
+      const uint64_t i = i0 + (uint64_t) q * nthreads;
+      ok[q] = i < total;
+      w[q] = ok[q] ? P.startw[i] : 0u;
+      uint32_t gg = 0;
+      while (ok[q] && gg + 1 < P.fnum && i >= P.woff[gg + 1]) ++gg;
+      g[q] = gg;
+      j[q] = ok[q] ? i - P.woff[gg] : 0;
     }
-    ((uint32_t*) msend[g])[j] = out;
+#pragma unroll
+    for (int q = 0; q < kB; ++q) {
+      const size_t at = (size_t) g[q] * P.iv_words + w[q];
+      sel[q] = ok[q] ? P.mask[at] : 0u;
+      skip[q] = ok[q] ? (uint32_t) (32 * j[q] - P.pref[at]) : 0u;
+      val[q] = ok[q] ? bitmap[w[q]] : 0u;
+      const uint64_t nbits = P.off[g[q] + 1] - P.off[g[q]];
+      need[q] = ok[q] ? (uint32_t) ((nbits - 32 * j[q]) < 32 ? (nbits - 32 * j[q]) : 32) : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < kB; ++q) {
+      if (!ok[q]) continue;
+      const uint32_t* mask = P.mask + (size_t) g[q] * P.iv_words;
+      uint32_t out = 0, k = 0, ww = w[q], s_ = sel[q], v_ = val[q], sk = skip[q];
+      if (sk == 0 && s_ == 0xFFFFFFFFu && need[q] == 32) {   // dense fast path
+        out = v_;
+      } else {
+        for (;;) {
+          while (sk && s_) {
+            s_ &= s_ - 1;
+            --sk;
+          }
+          while (s_ && k < need[q]) {
+            const uint32_t b = __ffs(s_) - 1;
+            out |= ((v_ >> b) & 1u) << k;
+            ++k;
+            s_ &= s_ - 1;
+          }
+          if (k >= need[q]) break;
+          ++ww;
+          s_ = mask[ww];
+          v_ = bitmap[ww];
+        }
+      }
+      ((uint32_t*) msend[g[q]])[j[q]] = out;
+    }
   }
   return wrote;
 }
