@@ -90,3 +90,15 @@ def test_oracle_equals_reference_on_rmat(rmat_file):
         got = refdriver.parse_output(t)[1]
         want = g.pagerank(0.85, 10, mode)
         assert np.max(np.abs(got - want) / want) < 1e-12
+
+
+def test_reference_repeated_queries_same_result(rmat_file):
+    """bench.py's CPU arm runs warm-up + timed queries in ONE ref_driver process
+    (fresh reference worker per query on the same loaded fragment)."""
+    path, g = rmat_file
+    s = g.max_degree_vertex()
+    info, t = refdriver.run_app("bfs", path, source=s, threads=4, repeat=3)
+    assert len(info["query_ms"]) == 3
+    assert np.array_equal(refdriver.parse_output(t, int)[1], g.bfs(s)[0])
+    info, _ = refdriver.run_app("pagerank", path, threads=2, repeat=2, want_output=False)
+    assert len(info["query_ms"]) == 2
