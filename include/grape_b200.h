@@ -234,6 +234,11 @@ int gl_comm_export(gl_comm_t*, void* handles_out, size_t bytes);
 /* all_handles: fnum consecutive exports, ordered by fid */
 int gl_comm_open(gl_comm_t*, const void* all_handles, size_t bytes);
 void gl_comm_destroy(gl_comm_t*);
+/* Diagnostic: average time (us) of one kernel that stores `bytes` from local
+ * memory into the next peer's (all_peers = 0) or every peer's (1) mirror slot
+ * with 16-byte (vec16 = 1) or 4-byte stores, followed by a fence.sys per CTA.
+ * Sizes the multi-GPU design decisions in DESIGN.md section 5. */
+int gl_comm_peer_write_us(gl_comm_t*, size_t bytes, int vec16, int all_peers, int reps, double* us_out);
 
 /* ------------------------------------------------------------------ *
  * PIE apps (PEval / IncEval / Output): replaces GPUWorker::{Init,Query}

@@ -83,7 +83,7 @@ SYMBOLS = [
     "gl_frag_build_rmat", "gl_rmat_edges_host", "gl_frag_get_info", "gl_frag_view_get", "gl_frag_copy_csr",
     "gl_frag_copy_ovgid", "gl_frag_oid2lid", "gl_frag_max_degree_vertex", "gl_frag_offload",
     "gl_frag_reload", "gl_frag_destroy", "gl_comm_create", "gl_comm_export", "gl_comm_open",
-    "gl_comm_destroy", "gl_app_config_default", "gl_app_create", "gl_app_query", "gl_app_result",
+    "gl_comm_destroy", "gl_comm_peer_write_us", "gl_app_config_default", "gl_app_create", "gl_app_query", "gl_app_result",
     "gl_app_result_oids", "gl_app_destroy", "gl_edge_scan_queue", "gl_compact_bitmap", "gl_dev_alloc",
     "gl_dev_free", "gl_dev_memset", "gl_dev_h2d", "gl_dev_d2h", "gl_dev_sync", "gl_kernel_launch_count",
     "gl_host_alloc_pinned", "gl_host_free_pinned",
@@ -294,6 +294,11 @@ class Comm:
     def open(self, all_handles):
         blob = b"".join(all_handles)
         check(lib().gl_comm_open(self.h, blob, len(blob)))
+
+    def peer_write_us(self, nbytes, vec16=True, all_peers=False, reps=20):
+        us = C.c_double()
+        check(lib().gl_comm_peer_write_us(self.h, C.c_size_t(nbytes), int(vec16), int(all_peers), int(reps), C.byref(us)))
+        return us.value
 
     def close(self):
         if self.h:

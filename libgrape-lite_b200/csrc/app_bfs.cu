@@ -273,42 +273,6 @@ k_bfs_pull(PullArgs a, const uint32_t* __restrict__ cur, uint32_t* vis,
   flush_acc(acc, ctrl);
 }
 
-// Pull step over the outer vertices (bfs.h:210-223): an unvisited outer vertex
-// whose reverse adjacency holds a frontier vertex joins level depth+1 and is
-// reported to its owner.
-__global__ void __launch_bounds__(kTB)
-k_bfs_pull_outer(const uint64_t* __restrict__ orp, const uint32_t* __restrict__ ocol,
-                 uint32_t ivnum, uint32_t ovnum, const uint32_t* __restrict__ cur,
-                 uint32_t* vis, uint32_t* nxt, uint32_t* remote, ScanCtrl* ctrl) {
-  ScanAcc acc;
-  uint64_t scanned = 0;
-  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < ovnum;
-       o += gridDim.x * blockDim.x) {
-    const uint32_t v = ivnum + o;
-    if (bit_test(vis, v)) continue;
-    uint64_t b = orp[o], e = orp[o + 1], p = b;
-    bool found = false;
-    for (; p < e; ++p) {
-      if (bit_test(cur, ocol[p])) {
-        found = true;
-        ++p;
-        break;
-      }
-    }
-    scanned += p - b;
-    if (found) {
-      bit_set_atomic(vis, v);
-      bit_set_atomic(nxt, v);
-      bit_set_atomic(remote, v);
-      acc.remote++;
-      acc.touched++;
-    }
-  }
-  flush_acc(acc, ctrl);
-  unsigned long long s = warp_sum((unsigned long long) scanned);
-  if (lane_id() == 0 && s) atomicAdd(&ctrl->scanned, s);
-}
-
 // ---------------------------------------------------------------------------
 // Fused whole-query BFS (single fragment): ONE cooperative launch runs every
 // superstep.  Per-level device timestamps keep the ms/superstep report.

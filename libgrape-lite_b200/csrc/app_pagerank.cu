@@ -108,27 +108,6 @@ __global__ void k_pr_permute_cols(const uint32_t* __restrict__ col, uint64_t m,
   }
 }
 
-// pull: one warp per row chunk; lanes stride the row, fixed-order tree sum
-__global__ void __launch_bounds__(kTB)
-k_pr_pull(const uint64_t* __restrict__ rp, const uint32_t* __restrict__ col,
-          const double* __restrict__ contrib, double* next, uint32_t ivnum,
-          double base, double delta, ScanCtrl* ctrl) {
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  uint64_t scanned = 0;
-  for (uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < ivnum; v += warps) {
-    uint64_t b = rp[v], e = rp[v + 1];
-    double s = 0;
-    for (uint64_t p = b + lane_id(); p < e; p += 32) s += contrib[col[p]];
-    s = warp_sum(s);
-    if (lane_id() == 0) {
-      next[v] = base + delta * s;
-      scanned += e - b;
-    }
-  }
-  if (lane_id() == 0 && scanned) atomicAdd(&ctrl->scanned, (unsigned long long) scanned);
-}
-
-// ship partial sums of outer vertices (pagerank.h:227-238)
 __global__ void __launch_bounds__(kTB)
 k_pr_send(double* next, uint32_t ivnum, uint32_t ovnum,
           const uint32_t* __restrict__ ovgid, MsgView mv) {
@@ -267,8 +246,6 @@ struct PageRankApp : gl_app {
     const double N = (double) fv.total_vnum;
     const double base = (1.0 - cfg.pr_delta) / N + cfg.pr_delta * dangling / N;
     if (cfg.pr_pull) {
-      static thread_local int gp = 0;
-      if (!gp) gp = persistent_grid(k_pr_pull, eng.sm_count);
       if (fv.ivnum) {
         GL_LAUNCH(k_pr_contrib, (fv.ivnum + 255) / 256, 256, s, rank, fv.oe_rp, fv.ivnum, perm, contrib);
       }
@@ -285,7 +262,6 @@ struct PageRankApp : gl_app {
           GL_LAUNCH(k_dense_pull<OpPrPull>, grid, kTB, s, fv.oe_rp, col_p ? col_p : fv.oe_col, (const void*) nullptr, frag->oe_tile_row,
                     frag->oe_ntiles, fv.ivnum, (uint64_t) frag->oe.entries, op, eng.ctrl);
         }
-        (void) gp;
       }
     } else {
       if (fv.ivnum) GL_LAUNCH(k_pr_base, (fv.ivnum + 255) / 256, 256, s, next, fv.ivnum, base);

@@ -688,3 +688,63 @@ void gl_comm_destroy(gl_comm_t* c) {
 }
 
 }  // extern "C"
+
+// ---- diagnostic: kernel-driven NVLink peer-store bandwidth --------------------
+namespace gl {
+namespace {
+template <typename V>
+__global__ void __launch_bounds__(256) k_peer_write(const V* __restrict__ src, V* const* dsts, uint32_t ndst, size_t n) {
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (uint32_t d = 0; d < ndst; ++d) {
+    V* dst = dsts[d];
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
+}
+}  // namespace
+}  // namespace gl
+
+extern "C" int gl_comm_peer_write_us(gl_comm_t* c, size_t bytes, int vec16, int all_peers, int reps, double* us_out) {
+  using namespace gl;
+  GL_ARG(c && us_out && reps > 0, "gl_comm_peer_write_us: null argument");
+  if (!c->opened || c->fnum < 2) {
+    set_error("gl_comm_peer_write_us needs an opened communicator with fnum >= 2");
+    return GL_ERR_STATE;
+  }
+  bytes &= ~(size_t) 15;
+  if (bytes == 0 || bytes > c->mirror_bytes) {
+    set_error("gl_comm_peer_write_us: bytes must be in (0, mirror_bytes]");
+    return GL_ERR_ARG;
+  }
+  void* src = nullptr;
+  GL_CUDA(cudaMalloc(&src, bytes));
+  GL_CUDA(cudaMemset(src, 1, bytes));
+  std::vector<char*> dsts;
+  for (uint32_t k = 1; k < c->fnum; ++k) {
+    const uint32_t p = (c->fid + k) % c->fnum;
+    dsts.push_back(c->peer_base[p] + c->mirror_off(1, c->fid));   // my parity-1 mirror slot at peer p
+    if (!all_peers) break;
+  }
+  char** d_dsts = nullptr;
+  GL_CUDA(cudaMalloc(&d_dsts, sizeof(char*) * dsts.size()));
+  GL_CUDA(cudaMemcpy(d_dsts, dsts.data(), sizeof(char*) * dsts.size(), cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  GL_CUDA(cudaEventCreate(&e0));
+  GL_CUDA(cudaEventCreate(&e1));
+  for (int r = -2; r < reps; ++r) {
+    if (r == 0) GL_CUDA(cudaEventRecord(e0, 0));
+    if (vec16) k_peer_write<uint4><<<148 * 4, 256>>>((const uint4*) src, (uint4* const*) d_dsts, (uint32_t) dsts.size(), bytes / 16);
+    else k_peer_write<uint32_t><<<148 * 4, 256>>>((const uint32_t*) src, (uint32_t* const*) d_dsts, (uint32_t) dsts.size(), bytes / 4);
+  }
+  GL_CUDA(cudaEventRecord(e1, 0));
+  GL_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  GL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *us_out = (double) ms * 1e3 / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_dsts);
+  cudaFree(src);
+  return GL_OK;
+}
