@@ -156,9 +156,11 @@ def run_gpu(args):
         cfg.setdefault("reserved", {})[1] = 1
     if args.app in ("pagerank", "cdlp"):
         cfg["max_round"] = 10
-    if args.app == "pagerank" and args.pr_pull:
+    if args.app == "pagerank" and (args.pr_pull or args.pr_f32):
         cfg["pr_pull"] = 1
-    app = pkg.App(args.app, frag, comm, **cfg)
+        if args.pr_f32:
+            cfg.setdefault("reserved", {})[5] = 1
+    app = pkg.App("wcc_opt" if (args.app == "wcc" and args.wcc_opt) else args.app, frag, comm, **cfg)
 
     pinned = pkg.PinnedBuffer(8 * max(frag.ivnum, 1))
     out = pinned.array(pkg.capi.RESULT_DTYPE[app.kind], frag.ivnum)
@@ -356,6 +358,8 @@ def main():
     ap.add_argument("--push-only", action="store_true")
     ap.add_argument("--cpu-scale", type=int, default=22, help="largest scale the CPU arm runs (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wcc-opt", action="store_true", help="WCC by union-find (the reference's wcc_opt) instead of label propagation")
+    ap.add_argument("--pr-f32", action="store_true", help="PageRank pull gathering f32 contributions (f64 sums)")
     ap.add_argument("--no-hub-order", action="store_true", help="disable the hub-first shadow CSR (BFS)")
     ap.add_argument("--bfs-beta", type=int, default=0, help="BFS pull->push threshold divisor (0 = library default)")
     ap.add_argument("--pr-pull", action="store_true", help="PageRank: deterministic pull step instead of atomicAdd push")

@@ -251,7 +251,8 @@ typedef enum {
   GL_APP_WCC = 2,      /* cuda/wcc/wcc.h        result: int64 oid of min-gid   */
   GL_APP_PAGERANK = 3, /* cuda/pagerank/pagerank.h result: double              */
   GL_APP_CDLP = 4,     /* cuda/cdlp/cdlp.h      result: int64 label            */
-  GL_APP_LCC = 5       /* cuda/lcc/lcc_opt.h    result: double                 */
+  GL_APP_LCC = 5,      /* cuda/lcc/lcc_opt.h    result: double                 */
+  GL_APP_WCC_OPT = 6   /* cuda/wcc/wcc_opt.h (union-find) result: as GL_APP_WCC  */
 } gl_app_kind;
 
 typedef struct {

@@ -88,4 +88,5 @@ gl_app* make_wcc();
 gl_app* make_pagerank();
 gl_app* make_cdlp();
 gl_app* make_lcc();
+gl_app* make_wcc_opt();
 }  // namespace gl

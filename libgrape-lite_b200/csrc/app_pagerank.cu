@@ -62,15 +62,21 @@ __global__ void k_pr_base(double* next, uint32_t ivnum, double base) {
 }
 
 // pull as an edge-balanced dense sweep: next[row] += delta * sum contrib[col]
+// CT = double, or float: the gathered array then is 4 B per vertex (67 MB at
+// 2^24 vertices: it FITS the 126 MB L2, the f64 one does not).  Sums stay f64;
+// every term carries a relative rounding error <= 2^-24, so after the damped
+// iteration the result is within 2^-24 / (1 - delta) = 4e-7 of the f64 run
+// (parity bar: 1e-6).
+template <typename CT>
 struct OpPrPull {
   using Val = double;
   using W = float;
   static constexpr bool kWeighted = false;
-  const double* contrib;
+  const CT* contrib;
   double* next;
   double delta;
   GL_DEV Val identity() const { return 0.0; }
-  GL_DEV Val entry(uint32_t v, W) const { return __ldcg(contrib + v); }
+  GL_DEV Val entry(uint32_t v, W) const { return (double) __ldcg(contrib + v); }
   GL_DEV Val combine(Val a, Val b) const { return a + b; }
   GL_DEV void flush(uint32_t row, Val part, ScanAcc&) const { atomicAdd(next + row, delta * part); }
 };
@@ -79,12 +85,13 @@ struct OpPrPull {
 // permutation: the gathered array is then ordered by descending degree, so the
 // few thousand hub entries that receive most of the 5e8 random reads of a
 // sweep are contiguous and stay in L1/L2 (the 134 MB array does not fit L2).
+template <typename CT>
 __global__ void k_pr_contrib(const double* rank, const uint64_t* rp,
-                             uint32_t ivnum, const uint32_t* __restrict__ perm, double* contrib) {
+                             uint32_t ivnum, const uint32_t* __restrict__ perm, CT* contrib) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < ivnum) {
     uint64_t dg = rp[i + 1] - rp[i];
-    contrib[perm ? perm[i] : i] = dg ? rank[i] / (double) dg : 0.0;
+    contrib[perm ? perm[i] : i] = (CT) (dg ? rank[i] / (double) dg : 0.0);
   }
 }
 __global__ void k_pr_degkey(const uint64_t* rp, uint32_t n, uint32_t* key, uint32_t* val) {
@@ -226,6 +233,28 @@ struct PageRankApp : gl_app {
     return GL_OK;
   }
 
+  // contributions -> (mirror sync) -> next = base + delta * gathered sums
+  template <typename CT>
+  int pull_sweep(cudaStream_t s, double base) {
+    CT* cb = (CT*) contrib;
+    if (fv.ivnum) GL_LAUNCH(k_pr_contrib<CT>, (fv.ivnum + 255) / 256, 256, s, rank, fv.oe_rp, fv.ivnum, perm, cb);
+    // outer copies take their owner's contribution (dense mirror sync)
+    if (fv.fnum > 1) GL_TRY(mm.SyncValuesToGhosts(s, cb, (int) sizeof(CT)));
+    if (fv.ivnum) {
+      // next = base, then the TMA-staged dense sweep folds the gathered sums in
+      GL_LAUNCH(k_pr_base, (fv.ivnum + 255) / 256, 256, s, next, fv.ivnum, base);
+      static thread_local int gd = 0;
+      if (!gd) gd = persistent_grid(k_dense_pull<OpPrPull<CT>>, eng.sm_count);
+      if (frag->oe_ntiles) {
+        OpPrPull<CT> op{cb, next, cfg.pr_delta};
+        int grid = (int) std::min<uint32_t>((uint32_t) gd, frag->oe_ntiles);
+        GL_LAUNCH(k_dense_pull<OpPrPull<CT>>, grid, kTB, s, fv.oe_rp, col_p ? col_p : fv.oe_col, (const void*) nullptr,
+                  frag->oe_tile_row, frag->oe_ntiles, fv.ivnum, (uint64_t) frag->oe.entries, op, eng.ctrl);
+      }
+    }
+    return GL_OK;
+  }
+
   int IncEval() override {
     cudaStream_t s = eng.stream;
     if (fv.fnum > 1) {
@@ -246,23 +275,8 @@ struct PageRankApp : gl_app {
     const double N = (double) fv.total_vnum;
     const double base = (1.0 - cfg.pr_delta) / N + cfg.pr_delta * dangling / N;
     if (cfg.pr_pull) {
-      if (fv.ivnum) {
-        GL_LAUNCH(k_pr_contrib, (fv.ivnum + 255) / 256, 256, s, rank, fv.oe_rp, fv.ivnum, perm, contrib);
-      }
-      // outer copies take their owner's contribution (dense mirror sync)
-      if (fv.fnum > 1) GL_TRY(mm.SyncValuesToGhosts(s, contrib, 8));
-      if (fv.ivnum) {
-        // next = base, then the TMA-staged dense sweep folds the gathered sums in
-        GL_LAUNCH(k_pr_base, (fv.ivnum + 255) / 256, 256, s, next, fv.ivnum, base);
-        static thread_local int gd = 0;
-        if (!gd) gd = persistent_grid(k_dense_pull<OpPrPull>, eng.sm_count);
-        if (frag->oe_ntiles) {
-          OpPrPull op{contrib, next, cfg.pr_delta};
-          int grid = (int) std::min<uint32_t>((uint32_t) gd, frag->oe_ntiles);
-          GL_LAUNCH(k_dense_pull<OpPrPull>, grid, kTB, s, fv.oe_rp, col_p ? col_p : fv.oe_col, (const void*) nullptr, frag->oe_tile_row,
-                    frag->oe_ntiles, fv.ivnum, (uint64_t) frag->oe.entries, op, eng.ctrl);
-        }
-      }
+      if (cfg.reserved[5] == 1) GL_TRY(pull_sweep<float>(s, base));
+      else GL_TRY(pull_sweep<double>(s, base));
     } else {
       if (fv.ivnum) GL_LAUNCH(k_pr_base, (fv.ivnum + 255) / 256, 256, s, next, fv.ivnum, base);
       OpPrPush op{rank, next, fv.oe_rp, cfg.pr_delta};

@@ -30,7 +30,7 @@ def main():
         dist.all_gather_object(out, arr)
         return np.concatenate(out)
 
-    for wmode, apps in ((0, ["bfs", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp"])):
+    for wmode, apps in ((0, ["bfs", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "wcc_opt", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp"])):
         n = 1 << scale
         frag = pkg.Fragment.rmat(scale, 16, seed=17, weight_mode=wmode, fid=rank, fnum=world)
         comm = gdist.make_comm(rank, world, frag.ivnum)
@@ -68,7 +68,7 @@ def main():
                     ok = np.array_equal(got, g.bfs(source)[0])
                 elif kind == "sssp":
                     ok = np.array_equal(got, g.sssp(source)[0])
-                elif kind == "wcc":
+                elif kind in ("wcc", "wcc_opt"):
                     ok = np.array_equal(got, g.wcc()[0].astype(np.int64))
                 elif kind == "cdlp":
                     ok = np.array_equal(got, g.cdlp(5))

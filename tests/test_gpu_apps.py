@@ -168,11 +168,12 @@ def test_sssp_real_weights_f32_within_tolerance():
 
 
 # ------------------------------------------------------------------- WCC ----
-def test_wcc_golden(p2p):
+@pytest.mark.parametrize("kind", ["wcc", "wcc_opt"])
+def test_wcc_golden(p2p, kind):
     oids, und, dr = p2p
     want = np.array([int(v) for _, v in G.golden_pairs("p2p-31-WCC")])
     for frag in (und, dr):
-        app = app_available("wcc", frag)
+        app = app_available(kind, frag)
         app.query()
         lab = app.result()
         assert G.same_partition(lab, want)          # misc/wcc_check.cc rule
@@ -181,25 +182,64 @@ def test_wcc_golden(p2p):
         app.close()
 
 
+@pytest.mark.parametrize("kind", ["wcc", "wcc_opt"])
 @pytest.mark.parametrize("scale", [10, 15])
-def test_wcc_rmat_vs_oracle(scale):
+def test_wcc_rmat_vs_oracle(scale, kind):
     n, src, dst, _ = rmat_graph(scale, seed=6)
     g = pyoracle.Graph(n, src, dst, None)
     frag = pkg().Fragment.rmat(scale, 16, seed=6)
-    app = app_available("wcc", frag)
+    app = app_available(kind, frag)
     app.query()
     want, _ = g.wcc()
     assert np.array_equal(app.result(), want.astype(np.int64))   # bit-exact min labels
+    app.query()                                                   # a second query resets the state
+    assert np.array_equal(app.result(), want.astype(np.int64))
+    app.close()
+    frag.close()
+
+
+@pytest.mark.parametrize("kind", ["wcc", "wcc_opt"])
+@pytest.mark.parametrize("directed", [False, True])
+def test_wcc_many_components(kind, directed):
+    """Two large components (one of them a star whose centre has the LARGEST id),
+    a long path, small cliques, isolated vertices, self loops and a multi-edge:
+    the union-find app must not depend on one giant component being present."""
+    rng = np.random.RandomState(5)
+    parts_s, parts_d = [], []
+    a = rng.randint(0, 3000, size=12000)                       # dense random blob on [0, 3000)
+    b = rng.randint(0, 3000, size=12000)
+    parts_s.append(a); parts_d.append(b)
+    parts_s.append(np.full(2999, 6999)); parts_d.append(np.arange(4000, 6999))   # star, centre 6999
+    parts_s.append(np.arange(7000, 7999)); parts_d.append(np.arange(7001, 8000))  # path 7000..7999
+    for base in range(8000, 8100, 4):                           # 4-cliques
+        for i in range(4):
+            for j in range(i + 1, 4):
+                parts_s.append(np.array([base + j])); parts_d.append(np.array([base + i]))
+    parts_s.append(np.array([8200, 8201, 8201])); parts_d.append(np.array([8200, 8202, 8202]))  # loop + multi-edge
+    src = np.concatenate(parts_s).astype(np.int64)
+    dst = np.concatenate(parts_d).astype(np.int64)
+    n = 8300                                                    # 8203.. are isolated
+    g = pyoracle.Graph(n, src, dst, None)                       # WCC ignores direction
+    frag = pkg().Fragment.from_edges(n, src, dst, directed=directed)
+    app = app_available(kind, frag)
+    app.query()
+    want, _ = g.wcc()
+    assert np.array_equal(app.result(), want.astype(np.int64))
     app.close()
     frag.close()
 
 
 # -------------------------------------------------------------- PageRank ----
-@pytest.mark.parametrize("pull", [0, 1])
+def _pr_cfg(pull):
+    """0 = push (f64 atomics), 1 = pull, 2 = pull gathering f32 contributions (f64 sums)"""
+    return dict(pr_pull=1 if pull else 0, reserved={5: 1} if pull == 2 else {})
+
+
+@pytest.mark.parametrize("pull", [0, 1, 2])
 def test_pagerank_golden(p2p, pull):
     oids, und, _ = p2p
     want = np.array([float(v) for _, v in G.golden_pairs("p2p-31-PR")])
-    app = app_available("pagerank", und, pr_delta=0.85, max_round=10, pr_pull=pull)
+    app = app_available("pagerank", und, pr_delta=0.85, max_round=10, **_pr_cfg(pull))
     app.query()
     got = app.result()
     assert G.eps_check(got, want, 1e-4)              # the reference's own check
@@ -207,19 +247,19 @@ def test_pagerank_golden(p2p, pull):
     app.close()
 
 
-@pytest.mark.parametrize("pull", [0, 1])
+@pytest.mark.parametrize("pull", [0, 1, 2])
 def test_pagerank_rmat_vs_oracle(pull):
     scale = 14
     n, src, dst, _ = rmat_graph(scale, seed=2)
     g = pyoracle.Graph(n, src, dst, None)
     frag = pkg().Fragment.rmat(scale, 16, seed=2)
-    app = app_available("pagerank", frag, pr_delta=0.85, max_round=10, pr_pull=pull)
+    app = app_available("pagerank", frag, pr_delta=0.85, max_round=10, **_pr_cfg(pull))
     st = app.query()
     got = app.result()
     for mode in (0, 1):
         want = g.pagerank(0.85, 10, mode)
         assert np.max(np.abs(got - want) / want) < 1e-6
-    assert abs(got.sum() - 1.0) < 1e-9
+    assert abs(got.sum() - 1.0) < (1e-6 if pull == 2 else 1e-9)
     assert st.supersteps == 12        # PEval + 10 updates + the final message round
     app.close()
     frag.close()
