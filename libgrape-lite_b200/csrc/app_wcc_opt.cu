@@ -179,11 +179,17 @@ __global__ void k_uf_labels_init(uint32_t* clabel, uint32_t ivnum, uint32_t ovnu
   if (i < ivnum) clabel[i] = (fid << fid_offset) | i;
   else if (i < ivnum + ovnum) clabel[i] = ovgid[i - ivnum];
 }
-__global__ void k_uf_labels_fold(const uint32_t* __restrict__ par, uint32_t* clabel, uint32_t tvnum) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// The root is the member with the smallest local index, i.e. the smallest gid
+// among the INNER members; only outer copies (gids of other fragments) can
+// lower the label.  The plain pre-check keeps the atomics off the hot word of
+// the giant component (16 M atomicMin on one address cost 5 ms).
+__global__ void k_uf_labels_fold(const uint32_t* __restrict__ par, uint32_t* clabel, uint32_t ivnum, uint32_t tvnum) {
+  const uint32_t i = ivnum + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= tvnum) return;
   const uint32_t r = par[i];
-  if (r != i) atomicMin(clabel + r, clabel[i]);   // clabel[i] of a non-root is still its own gid here
+  if (r == i) return;
+  const uint32_t g = clabel[i];   // clabel[i] of a non-root is still its own gid here
+  if (g < __ldcg(clabel + r)) atomicMin(clabel + r, g);
 }
 
 // an outer copy whose component label is better than what its owner was told
@@ -208,6 +214,7 @@ struct UfApply {
   uint32_t* clabel;
   GL_DEV void operator()(const ItemU32U32& it, ScanAcc& acc) const {
     const uint32_t r = par[it.lid];
+    if (!(it.val < __ldcg(clabel + r))) return;   // keep failing atomics off the giant component's word
     if (it.val < atomicMin(clabel + r, it.val)) acc.aux++;
   }
 };
@@ -310,7 +317,7 @@ struct WccOptApp : gl_app {
     if (tvnum) {
       GL_LAUNCH(k_uf_compress, g256, 256, s, par, tvnum);
       GL_LAUNCH(k_uf_labels_init, (tvnum + 255) / 256, 256, s, clabel, fv.ivnum, fv.ovnum, fv.ovgid, fv.fid, fv.fid_offset);
-      GL_LAUNCH(k_uf_labels_fold, (tvnum + 255) / 256, 256, s, par, clabel, tvnum);
+      if (fv.ovnum) GL_LAUNCH(k_uf_labels_fold, (fv.ovnum + 255) / 256, 256, s, par, clabel, fv.ivnum, tvnum);
     }
     q_touched += fv.ivnum;
     peval_entries = q_entries + (uint64_t) kSampled * fv.ivnum;
