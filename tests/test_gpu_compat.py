@@ -78,3 +78,15 @@ def test_wcc_partition(dataset, lb):
     got = np.array([int(l.split()[1]) for l in text.splitlines()])
     want = np.array([int(v) for _, v in G.golden_pairs("p2p-31-WCC")])
     assert G.same_partition(got, want)
+
+
+def test_engine_warp_and_block_variants():
+    """ForEachWithIndex{Warp,WarpShared,WarpDynamic,Block,BlockShared,BlockDynamic}
+    of the drop-in ParallelEngine (parallel_engine.h:93-271) with the functor
+    signatures the reference's CDLP / LCC sources use."""
+    exe = os.path.join(ROOT, "compat", "_build", "test_engine_variants")
+    if not os.path.exists(exe):
+        pytest.skip("compat/_build/test_engine_variants not built")
+    p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert p.returncode == 0 and "MISMATCH" not in p.stdout, p.stdout[-3000:]
+    assert p.stdout.count("OK") == 21
