@@ -264,8 +264,16 @@ typedef struct {
   double sssp_prio;      /* 0 -> reference heuristic 32*avg_w/avg_deg           */
   int direction_opt;     /* BFS: 0 push only, 1 push/pull (bfs.h:168-261)       */
   int pr_pull;           /* PageRank: 0 push (atomicAdd), 1 pull (deterministic)*/
-  int fuse_supersteps;   /* 1: run the superstep loop as one CUDA graph         */
-  int reserved[8];
+  int fuse_supersteps;   /* BFS: 1 = the whole query is ONE cooperative kernel per
+                            GPU (levels, direction switches and, on several
+                            fragments, the NVLink collectives happen inside it);
+                            0 = one superstep per host round                    */
+  int reserved[8];       /* tuning / test hooks, 0 = default:
+                            [0] 1: WCC dense rounds as pull sweeps
+                            [1] 1: BFS without the hub-first shadow CSR
+                            [2] BFS pull->push threshold divisor (default 24)
+                            [3] >=4: number of BFS level bitmaps (forces spills)
+                            [5] 1: PageRank pull gathers f32 contributions      */
 } gl_app_config;
 void gl_app_config_default(gl_app_config*);
 
