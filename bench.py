@@ -248,10 +248,11 @@ def run_gpu(args):
     dom = int(np.argmax(agg_ms))
     touched_dom = last[7] * (agg_ent[dom] / max(sum(agg_ent), 1.0))
     whole_balg = alg_bytes(args.app, last[5], last[6], last[7], weighted)
-    fused_query = args.app == "bfs" and world == 1 and not args.no_fuse
+    fused_query = args.app == "bfs" and not args.no_fuse
     if fused_query:
-        # the whole query is ONE launch (k_bfs_fused): the dominant kernel is the step
-        dom_name = "k_bfs_fused"
+        # the whole query is ONE cooperative launch per GPU: the dominant kernel is the step
+        # (world > 1: rank 0's launch; its algorithmic bytes are rank 0's share of the query)
+        dom_name = "k_bfs_fused" if world == 1 else "k_bfs_fused_multi"
         b_alg = whole_balg
         dom_ms = ms_per_step
     else:
