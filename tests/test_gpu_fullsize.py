@@ -1,0 +1,132 @@
+"""GPU, BASELINE.json's full size (R-MAT scale 24, edge factor 16): results are
+too large for the CPU oracle, so they are checked through size-independent
+properties of the domain, evaluated with numpy over the fragment's own CSR:
+
+* BFS  (Graph500 validation): depth[source] = 0; every CSR entry joins depths
+  that differ by at most 1; every reached vertex except the source has a
+  neighbour one level up; unreached vertices only touch unreached vertices;
+  fused / stepwise / push-only runs agree bit for bit.
+* WCC: a label is the smallest vertex of its class (label[label[v]] = label[v],
+  label[v] <= v), no edge joins two labels, and the union-find app (wcc_opt)
+  returns the same labels as label propagation (two independent algorithms).
+* SSSP (integer weights, exact in f32): no edge can improve a distance, every
+  reached vertex has a tight incoming edge.
+* PageRank: ranks sum to 1, the push (atomics) and pull (deterministic) forms agree
+  to 1e-6.
+GL_FULL_SCALE overrides the scale (default 24)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import pkg
+
+pytestmark = pytest.mark.gpu
+SCALE = int(os.environ.get("GL_FULL_SCALE", "24"))
+FAR = 1 << 30
+
+
+def _row_min_max(values_at_col, rp):
+    """per non-empty row: (rows, min, max) of values_at_col over the row's entries"""
+    deg = np.diff(rp.astype(np.int64))
+    rows = np.nonzero(deg > 0)[0]
+    starts = rp[:-1][rows].astype(np.int64)
+    return rows, np.minimum.reduceat(values_at_col, starts), np.maximum.reduceat(values_at_col, starts)
+
+
+@pytest.fixture(scope="module")
+def graph():
+    frag = pkg().Fragment.rmat(SCALE, 16, seed=1)
+    rp, col, _ = frag.csr(0)
+    yield frag, rp, col
+    frag.close()
+
+
+def test_bfs_full_size_properties(graph):
+    frag, rp, col = graph
+    n = frag.ivnum
+    source, _ = frag.max_degree_vertex()
+    results = {}
+    for name, cfg in (("fused", dict(fuse_supersteps=1)), ("stepwise", dict(fuse_supersteps=0)),
+                      ("push", dict(fuse_supersteps=1, direction_opt=0))):
+        app = pkg().App("bfs", frag, source_oid=int(source), **cfg)
+        app.query()
+        results[name] = app.result()
+        app.query()                                    # idempotent
+        assert np.array_equal(app.result(), results[name])
+        app.close()
+    d = results["fused"]
+    assert np.array_equal(d, results["stepwise"]) and np.array_equal(d, results["push"])
+    assert d[source] == 0
+    reached = d != np.iinfo(np.int64).max
+    d32 = np.where(reached, d, FAR).astype(np.int32)
+    rows, lo, hi = _row_min_max(d32[col], rp)
+    dv = d32[rows]
+    r = dv < FAR
+    assert np.all(lo[r] >= dv[r] - 1) and np.all(hi[r] <= dv[r] + 1)      # every edge spans <= 1 level
+    has_parent = lo[r] == dv[r] - 1
+    assert np.all(has_parent | (rows[r] == source))                       # a parent one level up
+    assert np.all(lo[~r] == FAR)                                          # unreached only touch unreached
+    deg = np.diff(rp.astype(np.int64))
+    assert np.all(reached[deg == 0] == (np.nonzero(deg == 0)[0] == source))  # isolated vertices stay unreached
+    assert reached.sum() > n // 2                                         # the giant component was traversed
+
+
+def test_wcc_full_size_properties(graph):
+    frag, rp, col = graph
+    n = frag.ivnum
+    labs = {}
+    for kind in ("wcc", "wcc_opt"):
+        app = pkg().App(kind, frag)
+        app.query()
+        labs[kind] = app.result()
+        app.close()
+    lab = labs["wcc"]
+    assert np.array_equal(lab, labs["wcc_opt"])          # label propagation == union-find
+    assert np.all(lab <= np.arange(n)) and np.all(lab >= 0)
+    assert np.array_equal(lab[lab], lab)                 # a label is its class's smallest vertex
+    l32 = lab.astype(np.int32)
+    rows, lo, hi = _row_min_max(l32[col], rp)
+    assert np.array_equal(lo, l32[rows]) and np.array_equal(hi, l32[rows])   # no edge joins two labels
+    deg = np.diff(rp.astype(np.int64))
+    iso = np.nonzero(deg == 0)[0]
+    assert np.array_equal(lab[iso], iso)                 # isolated vertices are their own class
+
+
+def test_sssp_full_size_properties():
+    scale = min(SCALE, 22)
+    frag = pkg().Fragment.rmat(scale, 16, seed=1, weight_mode=1)     # integer weights 1..255 (exact in f32)
+    rp, col, w = frag.csr(0)
+    source, _ = frag.max_degree_vertex()
+    app = pkg().App("sssp", frag, source_oid=int(source))
+    app.query()
+    dist = app.result()
+    app.close()
+    frag.close()
+    big = np.finfo(np.float64).max
+    reached = dist < big
+    assert dist[source] == 0.0
+    d = np.where(reached, dist, 1e18)
+    via = d[col] + w.astype(np.float64)                  # distance through each in-neighbour
+    rows, lo, _ = _row_min_max(via, rp)
+    r = reached[rows]
+    assert np.all(lo[r] >= d[rows][r])                   # no edge can improve a distance
+    tight = lo[r] == d[rows][r]
+    assert np.all(tight | (rows[r] == source))           # ... and one edge realises it
+    assert np.all(lo[~r] >= 1e18)                        # unreached only touch unreached
+    assert np.array_equal(dist[reached], np.round(dist[reached]))   # integer weights: exact sums
+
+
+def test_pagerank_full_size_properties():
+    scale = min(SCALE, 22)
+    frag = pkg().Fragment.rmat(scale, 16, seed=1)
+    out = {}
+    for name, cfg in (("push", dict(pr_pull=0)), ("pull", dict(pr_pull=1))):
+        app = pkg().App("pagerank", frag, pr_delta=0.85, max_round=10, **cfg)
+        app.query()
+        out[name] = app.result()
+        app.close()
+    frag.close()
+    for r in out.values():
+        assert abs(r.sum() - 1.0) < 1e-9 and np.all(r > 0)
+    assert np.max(np.abs(out["push"] - out["pull"]) / out["pull"]) < 1e-6
