@@ -20,6 +20,11 @@
 
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <thrust/device_vector.h>
+#include <thrust/host_vector.h>
+#include <thrust/pair.h>
+#include <thrust/binary_search.h>
+#include <thrust/execution_policy.h>
 
 #include <algorithm>
 #include <iomanip>
@@ -153,7 +158,181 @@ DEV_INLINE size_t atomicAdd64(size_t* address, size_t val) {
 DEV_INLINE int64_t atomicMin64(int64_t* address, int64_t val) {
   return (int64_t) atomicMin(reinterpret_cast<long long*>(address), (long long) val);
 }
+DEV_INLINE int64_t atomicCAS64(int64_t* address, int64_t compare, int64_t val) {
+  return (int64_t) atomicCAS(reinterpret_cast<unsigned long long*>(address), (unsigned long long) compare,
+                             (unsigned long long) val);
+}
+DEV_INLINE uint64_t atomicCAS64(uint64_t* address, uint64_t compare, uint64_t val) {
+  return (uint64_t) atomicCAS(reinterpret_cast<unsigned long long*>(address), (unsigned long long) compare,
+                              (unsigned long long) val);
+}
+
+// max / min over the lanes named by `mask`; every named lane gets the result
+// (dev_utils.h:110-138).  One shuffle per member: correct for any lane subset.
+template <typename T>
+DEV_INLINE T reduce_max_sync(uint32_t mask, T val) {
+  T best = val;
+  for (uint32_t m = mask; m; m &= m - 1) {
+    const T o = __shfl_sync(mask, val, __ffs(m) - 1);
+    best = o > best ? o : best;
+  }
+  return best;
+}
+template <typename T>
+DEV_INLINE T reduce_min_sync(uint32_t mask, T val) {
+  T best = val;
+  for (uint32_t m = mask; m; m &= m - 1) {
+    const T o = __shfl_sync(mask, val, __ffs(m) - 1);
+    best = o < best ? o : best;
+  }
+  return best;
+}
+
+// CTA-wide maximum delivered to every thread (dev_utils.h:281-293); the CTA
+// must call it converged, blockDim.x a multiple of 32.
+template <typename T>
+DEV_INLINE T blockAllReduceMax(T val) {
+  __shared__ T s_part[32];
+  __shared__ T s_all;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const T t = __shfl_xor_sync(0xffffffffu, val, o);
+    val = t > val ? t : val;
+  }
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();   // a previous call's readers are done with s_part / s_all
+  if (l == 0) s_part[w] = val;
+  __syncthreads();
+  if (w == 0) {
+    T v = s_part[l < nw ? l : 0];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const T t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = t > v ? t : v;
+    }
+    if (l == 0) s_all = v;
+  }
+  __syncthreads();
+  return s_all;
+}
+
+// Most-frequent-label counter of the CDLP app (dev_utils.h:384-470): an exact
+// open-addressing table in the CTA's 32 KB scratch (one probe; a busy slot sends
+// the label to a count-min sketch that only gives an upper bound), and an exact
+// linear-probing table in global memory for the vertices where that is not
+// enough.  The scratch layout is part of the interface — the app clears it
+// itself (cdlp.h:378-385): [ht_size keys of T][ht_size u32 counts][cms_k x
+// cms_size u32 sketch counters], per cooperative group `cid`.
+template <typename T>
+class MFLCounter {
+ public:
+  __device__ __forceinline__ void init(uint32_t* shm_data, T* global_data, uint32_t* global_cnt, int ht_size,
+                                       int cms_size, int cms_k, int cid, int csize, int width, T dft) {
+    uint32_t* mine = shm_data + (size_t) cid * ((size_t) (1 + width) * ht_size + (size_t) cms_size * cms_k);
+    keys_ = reinterpret_cast<T*>(mine);
+    cnts_ = mine + (size_t) ht_size * width;
+    sketch_ = cnts_ + ht_size;
+    ht_size_ = ht_size;
+    cms_size_ = cms_size;
+    cms_k_ = cms_k;
+    gkeys_ = global_data;
+    gcnts_ = global_cnt;
+    empty_ = dft;
+    (void) csize;
+  }
+  // count of `l` after this insertion, or -1 when its slot holds another label
+  __device__ __forceinline__ int insert_shm_ht(T l) {
+    const size_t at = slot(l, (size_t) ht_size_);
+    const T seen = atomicCAS64(keys_ + at, empty_, l);
+    if (seen != empty_ && seen != l) return -1;
+    return (int) atomicAdd(cnts_ + at, 1u) + 1;
+  }
+  __device__ __forceinline__ int query_shm_ht(T l) {
+    const size_t at = slot(l, (size_t) ht_size_);
+    return keys_[at] == l ? (int) cnts_[at] : -1;
+  }
+  // upper bound of the count of `l` (minimum over cms_k sketch rows)
+  __device__ __forceinline__ int insert_shm_cms(T l) {
+    uint32_t bound = 0x7fffffffu;
+    unsigned long long h = (unsigned long long) l;
+    for (int r = 0; r < cms_k_; ++r) {
+      h = (h ^ (h >> 31)) * 0x9E3779B97F4A7C15ull + (unsigned long long) r;
+      const uint32_t c = atomicAdd(sketch_ + (size_t) r * cms_size_ + (size_t) (h % (unsigned long long) cms_size_), 1u) + 1;
+      bound = c < bound ? c : bound;
+    }
+    return (int) bound;
+  }
+  // exact count of `l` in the vertex's private range [begin, end) of the global table
+  __device__ __forceinline__ int insert_global_ht(T l, size_t begin, size_t end) {
+    const size_t size = end - begin;
+    size_t at = slot(l, size);
+    for (;;) {
+      const T seen = atomicCAS64(gkeys_ + begin + at, empty_, l);
+      if (seen == empty_ || seen == l) break;
+      at = at + 1 == size ? 0 : at + 1;
+    }
+    return (int) atomicAdd(gcnts_ + begin + at, 1u) + 1;
+  }
+
+ private:
+  __device__ __forceinline__ static size_t slot(T l, size_t size) {
+    return (size_t) ((unsigned long long) l % (unsigned long long) size);
+  }
+  T* keys_;
+  uint32_t* cnts_;
+  uint32_t* sketch_;
+  int ht_size_, cms_size_, cms_k_;
+  T* gkeys_;
+  uint32_t* gcnts_;
+  T empty_;
+};
 }  // namespace dev
+
+namespace compat_detail {
+template <typename I>
+struct ToSizeT {
+  __host__ __device__ size_t operator()(const I& x) const { return (size_t) x; }
+};
+}  // namespace compat_detail
+
+// ---------------------------------------------------------- host utilities --
+// grape/cuda/utils/cuda_utils.h:262-333: segmented key sort and prefix sums
+// (temporary storage is allocated per call, as in the reference).
+template <typename T>
+T* SegmentSort(T* d_keys_in, T* d_keys_buffer, size_t* d_offset_lo, size_t* d_offset_hi, size_t num_items,
+               size_t num_segments) {
+  if (num_items == 0 || num_segments == 0) return d_keys_in;
+  cub::DoubleBuffer<T> keys(d_keys_in, d_keys_buffer);
+  size_t bytes = 0;
+  CHECK_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, keys, (int64_t) num_items, (int64_t) num_segments,
+                                                d_offset_lo, d_offset_hi));
+  void* tmp = nullptr;
+  CHECK_CUDA(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
+  CHECK_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp, bytes, keys, (int64_t) num_items, (int64_t) num_segments,
+                                                d_offset_lo, d_offset_hi));
+  CHECK_CUDA(cudaDeviceSynchronize());
+  CHECK_CUDA(cudaFree(tmp));
+  return keys.Current();
+}
+template <typename I, typename O>
+void InclusiveSum(I* d_in, O* d_out, size_t size, cudaStream_t stream) {
+  size_t bytes = 0;
+  CHECK_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, d_in, d_out, (int64_t) size, stream));
+  void* tmp = nullptr;
+  CHECK_CUDA(cudaMallocAsync(&tmp, std::max<size_t>(bytes, 16), stream));
+  CHECK_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, d_in, d_out, (int64_t) size, stream));
+  CHECK_CUDA(cudaFreeAsync(tmp, stream));
+}
+template <typename I, typename O>
+void ExclusiveSum64(I* d_in, O* d_out, size_t size, cudaStream_t stream) {   // accumulates in size_t
+  size_t bytes = 0;
+  cub::TransformInputIterator<size_t, compat_detail::ToSizeT<I>, I*> in(d_in, compat_detail::ToSizeT<I>());
+  CHECK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, d_out, (int64_t) size, stream));
+  void* tmp = nullptr;
+  CHECK_CUDA(cudaMallocAsync(&tmp, std::max<size_t>(bytes, 16), stream));
+  CHECK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, d_out, (int64_t) size, stream));
+  CHECK_CUDA(cudaFreeAsync(tmp, stream));
+}
 
 // ------------------------------------------------------------ shared value --
 // grape/cuda/utils/shared_value.h:28-80: device scalar with a host mirror
@@ -410,10 +589,23 @@ class Queue {
 // grape/cuda/fragment/device_fragment.h:36-450 — accessors over the SoA view
 namespace dev {
 
+// grape::Nbr plus the CSR position of the entry it was loaded from.  The
+// reference computes edge indices as `&nbr - row begin` in its AoS Nbr array
+// (device_fragment.h:398-421); with SoA storage the neighbour handed to an app
+// is a value, so it carries its position instead.
+template <typename VID_T, typename EDATA_T>
+struct PosNbr : public Nbr<VID_T, EDATA_T> {
+  using base_t = Nbr<VID_T, EDATA_T>;
+  DEV_HOST PosNbr() : base_t(), pos_(0) {}
+  DEV_HOST explicit PosNbr(VID_T v, uint64_t pos = 0) : base_t(v), pos_(pos) {}
+  DEV_HOST PosNbr(VID_T v, const EDATA_T& d, uint64_t pos = 0) : base_t(v, d), pos_(pos) {}
+  uint64_t pos_;
+};
+
 template <typename VID_T, typename EDATA_T>
 class AdjList {
  public:
-  using nbr_t = Nbr<VID_T, EDATA_T>;
+  using nbr_t = PosNbr<VID_T, EDATA_T>;
   class iterator {
    public:
     DEV_HOST iterator(const uint32_t* col, const EDATA_T* w, uint64_t pos) : col_(col), w_(w), pos_(pos) { load(); }
@@ -430,10 +622,10 @@ class AdjList {
    private:
     DEV_HOST_INLINE void load() { load_impl(std::is_same<EDATA_T, EmptyType>()); }
     DEV_HOST_INLINE void load_impl(std::true_type) {
-      if (col_) cur_ = nbr_t(col_[pos_]);
+      if (col_) cur_ = nbr_t(col_[pos_], pos_);
     }
     DEV_HOST_INLINE void load_impl(std::false_type) {
-      if (col_) cur_ = nbr_t(col_[pos_], w_ ? w_[pos_] : EDATA_T());
+      if (col_) cur_ = nbr_t(col_[pos_], w_ ? w_[pos_] : EDATA_T(), pos_);
     }
     const uint32_t* col_;
     const EDATA_T* w_;
@@ -460,7 +652,7 @@ template <typename OID_T, typename VID_T, typename VDATA_T, typename EDATA_T,
 class DeviceFragment {
  public:
   using vertex_t = Vertex<VID_T>;
-  using nbr_t = Nbr<VID_T, EDATA_T>;
+  using nbr_t = PosNbr<VID_T, EDATA_T>;
   using vertex_range_t = VertexRange<VID_T>;
   using adj_list_t = AdjList<VID_T, EDATA_T>;
   using const_adj_list_t = AdjList<VID_T, EDATA_T>;
@@ -526,6 +718,16 @@ class DeviceFragment {
     if (v.GetValue() < v_.ivnum) return (int) (v_.ie_rp[v.GetValue() + 1] - v_.ie_rp[v.GetValue()]);
     const VID_T o = v.GetValue() - v_.ivnum;
     return v_.ovie_rp ? (int) (v_.ovie_rp[o + 1] - v_.ovie_rp[o]) : 0;
+  }
+  // position of an entry inside the whole CSR / inside u's row
+  // (device_fragment.h:398-421)
+  DEV_INLINE size_t GetOutgoingEdgeIndex(const nbr_t& nbr) const { return (size_t) nbr.pos_; }
+  DEV_INLINE size_t GetOutgoingEdgeIndex(const vertex_t& u, const nbr_t& nbr) const {
+    return (size_t) (nbr.pos_ - v_.oe_rp[u.GetValue()]);
+  }
+  DEV_INLINE size_t GetIncomingEdgeIndex(const nbr_t& nbr) const { return (size_t) nbr.pos_; }
+  DEV_INLINE size_t GetIncomingEdgeIndex(const vertex_t& u, const nbr_t& nbr) const {
+    return (size_t) (nbr.pos_ - v_.ie_rp[u.GetValue()]);
   }
   DEV_INLINE adj_list_t GetOutgoingAdjList(const vertex_t& v) const {
     const VID_T u = v.GetValue();
@@ -835,12 +1037,12 @@ struct WeightOf<EmptyType> {
 };
 
 template <typename VID_T, typename EDATA_T, typename W>
-DEV_INLINE Nbr<VID_T, EDATA_T> make_nbr(uint32_t v, W w, std::false_type) {
-  return Nbr<VID_T, EDATA_T>((VID_T) v, (EDATA_T) w);
+DEV_INLINE dev::PosNbr<VID_T, EDATA_T> make_nbr(uint32_t v, W w, uint64_t pos, std::false_type) {
+  return dev::PosNbr<VID_T, EDATA_T>((VID_T) v, (EDATA_T) w, pos);
 }
 template <typename VID_T, typename EDATA_T, typename W>
-DEV_INLINE Nbr<VID_T, EDATA_T> make_nbr(uint32_t v, W, std::true_type) {
-  return Nbr<VID_T, EDATA_T>((VID_T) v);
+DEV_INLINE dev::PosNbr<VID_T, EDATA_T> make_nbr(uint32_t v, W, uint64_t pos, std::true_type) {
+  return dev::PosNbr<VID_T, EDATA_T>((VID_T) v, pos);
 }
 
 // adapter: (assign_op, edge_op(VertexMetadata, nbr)) -> engine Op.
@@ -863,13 +1065,14 @@ struct MetaOp {
     Vertex<vid_t> vu(u);
     return a(vu);
   }
+  static constexpr bool kWantsPos = true;   // the nbr handed to the app knows its CSR position
   template <typename M>
-  __device__ void edge(uint32_t u, const M& m, uint32_t v, W w, ::gl::ScanAcc&) const {
+  __device__ void edge_at(uint32_t u, const M& m, uint32_t v, W w, uint64_t pos, ::gl::ScanAcc&) const {
     EDGE_OP e = edge_op;
     VertexMetadata<vid_t, M> vm;
     vm.vertex = Vertex<vid_t>(u);
     vm.metadata = m;
-    e(vm, make_nbr<vid_t, edata_t, W>(v, w, std::is_same<edata_t, EmptyType>()));
+    e(vm, make_nbr<vid_t, edata_t, W>(v, w, pos, std::is_same<edata_t, EmptyType>()));
   }
 };
 // adapter: edge_op(vertex, nbr) -> engine Op
@@ -882,9 +1085,10 @@ struct PlainOp {
   static constexpr bool kWeighted = WeightOf<edata_t>::weighted;
   EDGE_OP edge_op;
   __device__ Meta assign(uint32_t) const { return 0; }
-  __device__ void edge(uint32_t u, Meta, uint32_t v, W w, ::gl::ScanAcc&) const {
+  static constexpr bool kWantsPos = true;   // the nbr handed to the app knows its CSR position
+  __device__ void edge_at(uint32_t u, Meta, uint32_t v, W w, uint64_t pos, ::gl::ScanAcc&) const {
     EDGE_OP e = edge_op;
-    e(Vertex<vid_t>(u), make_nbr<vid_t, edata_t, W>(v, w, std::is_same<edata_t, EmptyType>()));
+    e(Vertex<vid_t>(u), make_nbr<vid_t, edata_t, W>(v, w, pos, std::is_same<edata_t, EmptyType>()));
   }
 };
 

@@ -4,9 +4,9 @@
 // Mirrors examples/analytical_apps/run_cuda_app.h:110-138,182-317 (LoadGraph
 // -> CreateWorker -> Init -> Query -> Output) without gflags.
 //
-// usage: run_compat_app --application bfs|sssp|wcc|pagerank --efile F --vfile F
+// usage: run_compat_app --application bfs|sssp|wcc|pagerank|cdlp --efile F --vfile F
 //        --out_prefix DIR [--directed 0|1] [--bfs_source N] [--sssp_source N]
-//        [--pr_d D] [--pr_mr R] [--lb none|cm|wm|cta|strict|cmold]
+//        [--pr_d D] [--pr_mr R] [--cdlp_mr R] [--lb none|cm|wm|cta|strict|cmold]
 #include <sys/stat.h>
 
 #include <chrono>
@@ -23,6 +23,7 @@
 
 #include "cuda/app_config.h"
 #include "cuda/bfs/bfs.h"
+#include "cuda/cdlp/cdlp.h"
 #include "cuda/pagerank/pagerank.h"
 #include "cuda/sssp/sssp.h"
 #include "cuda/wcc/wcc.h"
@@ -61,7 +62,7 @@ int main(int argc, char** argv) {
   std::map<std::string, std::string> o = {{"application", "bfs"}, {"efile", ""},   {"vfile", ""},
                                           {"out_prefix", ""},     {"directed", "0"}, {"bfs_source", "0"},
                                           {"sssp_source", "0"},   {"pr_d", "0.85"},  {"pr_mr", "10"},
-                                          {"lb", "cta"}};
+                                          {"lb", "cta"},          {"cdlp_mr", "10"}};
   for (int i = 1; i + 1 < argc; i += 2) {
     std::string k = argv[i];
     if (k.rfind("--", 0) != 0 || !o.count(k.substr(2))) {
@@ -102,6 +103,11 @@ int main(int argc, char** argv) {
         rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kBothOutIn, gc::Pagerank>(comm_spec, o, app_config, std::stod(o["pr_d"]), std::stoi(o["pr_mr"]));
       else
         rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kOnlyOut, gc::Pagerank>(comm_spec, o, app_config, (float) std::stod(o["pr_d"]), std::stoi(o["pr_mr"]));
+    } else if (a == "cdlp") {
+      if (directed)
+        rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kBothOutIn, gc::CDLP>(comm_spec, o, app_config, std::stoi(o["cdlp_mr"]));
+      else
+        rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kOnlyOut, gc::CDLP>(comm_spec, o, app_config, std::stoi(o["cdlp_mr"]));
     } else {
       fprintf(stderr, "unknown application %s\n", a.c_str());
       rc = 2;

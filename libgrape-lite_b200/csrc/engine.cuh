@@ -21,6 +21,7 @@
 //    128-bit coalesced loads.
 //  * Every kernel is a persistent grid of (SMs x resident CTAs) blocks.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace gl {
@@ -103,6 +104,21 @@ GL_DEV T warp_sum(T v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Ops that need the CSR position of the entry they are handed (the reference's
+// GetOutgoingEdgeIndex(u, nbr) idiom: `&nbr - row begin`, device_fragment.h:398-421)
+// declare `static constexpr bool kWantsPos = true` and implement
+// edge_at(u, meta, v, w, pos, acc); everybody else keeps edge(u, meta, v, w, acc)
+// and compiles to exactly the same code as before.
+template <class Op, class = void>
+struct op_wants_pos : std::false_type {};
+template <class Op>
+struct op_wants_pos<Op, std::void_t<decltype(Op::kWantsPos)>> : std::integral_constant<bool, Op::kWantsPos> {};
+template <class Op, class M, class W>
+GL_DEV void call_edge(const Op& op, uint32_t u, const M& m, uint32_t v, W w, uint64_t pos, ScanAcc& acc) {
+  if constexpr (op_wants_pos<Op>::value) op.edge_at(u, m, v, w, pos, acc);
+  else op.edge(u, m, v, w, acc);
 }
 
 GL_DEV void flush_acc(const ScanAcc& a, ScanCtrl* c) {
@@ -278,7 +294,7 @@ GL_DEV void walk_tile(ScanSmem<typename Op::Meta>& sm, uint32_t nf, EdgeRange er
       uint64_t pos = sm.rp[lo] + (e - sm.pfx[lo]);
       uint32_t v = ld_stream_u32(er.col + pos);
       W w = Op::kWeighted ? load_w<W>(er.w, pos) : (W) 1;
-      op.edge(sm.v[lo], sm.meta[lo], v, w, acc);
+      call_edge(op, sm.v[lo], sm.meta[lo], v, w, pos, acc);
     }
   }
   if (threadIdx.x == 0) scanned += total;
@@ -347,7 +363,7 @@ GL_DEV void hub_scan_phase(uint32_t* s_item, EdgeRange er, const Op& op,
     for (uint64_t p = b + threadIdx.x; p < ab; p += kTB) {
       uint32_t v = ld_stream_u32(er.col + p);
       W w = Op::kWeighted ? load_w<W>(er.w, p) : (W) 1;
-      op.edge(h.v, meta, v, w, acc);
+      call_edge(op, h.v, meta, v, w, p, acc);
     }
     for (uint64_t p = ab + 4ull * threadIdx.x; p < ae; p += 4ull * kTB) {
       uint4 c = ld_stream_u4((const uint4*) (er.col + p));
@@ -356,15 +372,15 @@ GL_DEV void hub_scan_phase(uint32_t* s_item, EdgeRange er, const Op& op,
         const W* wp = (const W*) er.w + p;
         w0 = wp[0]; w1 = wp[1]; w2 = wp[2]; w3 = wp[3];
       }
-      op.edge(h.v, meta, c.x, w0, acc);
-      op.edge(h.v, meta, c.y, w1, acc);
-      op.edge(h.v, meta, c.z, w2, acc);
-      op.edge(h.v, meta, c.w, w3, acc);
+      call_edge(op, h.v, meta, c.x, w0, p, acc);
+      call_edge(op, h.v, meta, c.y, w1, p + 1, acc);
+      call_edge(op, h.v, meta, c.z, w2, p + 2, acc);
+      call_edge(op, h.v, meta, c.w, w3, p + 3, acc);
     }
     for (uint64_t p = ae + threadIdx.x; p < e; p += kTB) {
       uint32_t v = ld_stream_u32(er.col + p);
       W w = Op::kWeighted ? load_w<W>(er.w, p) : (W) 1;
-      op.edge(h.v, meta, v, w, acc);
+      call_edge(op, h.v, meta, v, w, p, acc);
     }
     if (threadIdx.x == 0) scanned += e - b;
   }
@@ -421,7 +437,7 @@ k_queue_scan_none(Src q, uint32_t n, EdgeRange er,
     uint64_t b = er.rp[u], e = er.rp[u + 1];
     for (uint64_t p = b; p < e; ++p) {
       W w = Op::kWeighted ? load_w<W>(er.w, p) : (W) 1;
-      op.edge(u, m, er.col[p], w, acc);
+      call_edge(op, u, m, er.col[p], w, p, acc);
     }
     scanned += e - b;
   }
@@ -479,7 +495,7 @@ k_queue_scan_warp(Src q, uint32_t n, EdgeRange er,
       if (active) {
         uint64_t p = (((uint64_t) bhi << 32) | blo) + (e - oex);
         W w = Op::kWeighted ? load_w<W>(er.w, p) : (W) 1;
-        op.edge(ou, om, er.col[p], w, acc);
+        call_edge(op, ou, om, er.col[p], w, p, acc);
       }
     }
     scanned += dg;
@@ -544,7 +560,7 @@ k_queue_scan_strict(Src q, uint32_t n,
     uint32_t u = q(lo);
     uint64_t pos = er.rp[u] + (e - pfx[lo]);
     W w = Op::kWeighted ? load_w<W>(er.w, pos) : (W) 1;
-    op.edge(u, op.assign(u), ld_stream_u32(er.col + pos), w, acc);
+    call_edge(op, u, op.assign(u), ld_stream_u32(er.col + pos), w, pos, acc);
   }
   flush_acc(acc, ctrl);
   if (threadIdx.x == 0 && hi_e > lo_e)

@@ -90,3 +90,12 @@ def test_engine_warp_and_block_variants():
     p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert p.returncode == 0 and "MISMATCH" not in p.stdout, p.stdout[-3000:]
     assert p.stdout.count("OK") == 21
+
+
+@pytest.mark.parametrize("lb", ["cm", "wm", "cta"])
+def test_cdlp_exact(dataset, lb):
+    """The reference's UNCHANGED cuda/cdlp/cdlp.h (gather through Get{Incoming,Outgoing}EdgeIndex,
+    SegmentSort, the shared-memory MFLCounter path, ForEachWithIndexBlockShared) on the compat
+    headers reproduces the golden labels (misc/cuda_app_tests.sh: ExactVerify p2p-31-CDLP)."""
+    info, text = run(dataset, "cdlp", lb, cdlp_mr=10)
+    assert text == G.golden_lines("p2p-31-CDLP")
