@@ -216,6 +216,138 @@ DEV_INLINE T blockAllReduceMax(T val) {
   return s_all;
 }
 
+// warp / CTA sums delivered to every lane / thread (dev_utils.h:219-247)
+template <typename T>
+DEV_INLINE T warp_reduce(T val) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+  return val;
+}
+template <typename T>
+DEV_INLINE T block_reduce(T val) {
+  __shared__ T s_part[32];
+  __shared__ T s_all;
+  val = warp_reduce(val);
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) s_part[w] = val;
+  __syncthreads();
+  if (w == 0) {
+    T v = l < nw ? s_part[l] : T(0);
+    v = warp_reduce(v);
+    if (l == 0) s_all = v;
+  }
+  __syncthreads();
+  return s_all;
+}
+
+// Bucketed set in the CTA's 32 KB scratch (dev_utils.h:491-556), as the LCC app
+// lays it out (lcc_opt.h:190-204): the first `bucket_stride` words are the fill
+// counts of all buckets of the CTA, row r of the table follows at
+// (1 + r) * bucket_stride; a cooperative group owns buckets [offset, offset +
+// bucket_num).  Entries beyond `cached_size` per bucket go to the CTA's slice of
+// a global overflow area.
+template <typename T>
+class ShmHashTable {
+ public:
+  __device__ __forceinline__ void init(T* shm_data, T* global_data, int offset, int bucket_size, int cached_size,
+                                       int bucket_num, int bucket_stride) {
+    fill_ = shm_data;
+    rows_ = shm_data + bucket_stride;
+    spill_ = global_data + (size_t) blockIdx.x * bucket_stride * (size_t) (bucket_size - cached_size);
+    base_ = offset;
+    cap_ = bucket_size;
+    cached_ = cached_size;
+    nb_ = bucket_num;
+    stride_ = bucket_stride;
+  }
+  __device__ __forceinline__ void clear(int thread_lane, int csize) {
+    for (int b = thread_lane; b < nb_; b += csize) fill_[base_ + b] = 0;
+  }
+  __device__ __forceinline__ bool insert(T x) {
+    const int b = base_ + (int) (x & (T) (nb_ - 1));
+    const int at = (int) atomicAdd(fill_ + b, (T) 1);
+    if (at < cached_) rows_[(size_t) at * stride_ + b] = x;
+    else if (at < cap_) spill_[(size_t) (at - cached_) * stride_ + b] = x;
+    else return false;
+    return true;
+  }
+  __device__ __forceinline__ bool lookup(T x) const {
+    const int b = base_ + (int) (x & (T) (nb_ - 1));
+    int n = (int) fill_[b];
+    if (n > cap_) n = cap_;
+    const int in_shm = n < cached_ ? n : cached_;
+    for (int r = 0; r < in_shm; ++r)
+      if (rows_[(size_t) r * stride_ + b] == x) return true;
+    for (int r = in_shm; r < n; ++r)
+      if (spill_[(size_t) (r - cached_) * stride_ + b] == x) return true;
+    return false;
+  }
+
+ private:
+  T* fill_;
+  T* rows_;
+  T* spill_;
+  int base_, cap_, cached_, nb_, stride_;
+};
+
+// |A ∩ B| of two ascending arrays, counted cooperatively by a warp / a CTA: the
+// shorter array is probed into the longer one by binary search; `callback(key)`
+// runs once per match (dev_utils.h:558-706).  Every lane / thread gets the total.
+template <typename T>
+DEV_INLINE bool sorted_contains(const T* a, size_t n, T key) {
+  size_t lo = 0, hi = n;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && a[lo] == key;
+}
+template <typename T, typename Y>
+DEV_INLINE size_t intersect_num(T* a, size_t size_a, T* b, size_t size_b, Y callback) {
+  const T* probe = a;
+  const T* hay = b;
+  size_t np = size_a, nh = size_b;
+  if (size_a > size_b) {
+    probe = b;
+    hay = a;
+    np = size_b;
+    nh = size_a;
+  }
+  size_t mine = 0;
+  if (nh)
+    for (size_t i = threadIdx.x & 31; i < np; i += 32) {
+      const T key = probe[i];
+      if (sorted_contains(hay, nh, key)) {
+        ++mine;
+        callback(key);
+      }
+    }
+  return warp_reduce(mine);
+}
+template <typename T, typename Y>
+DEV_INLINE size_t intersect_num_blk(T* a, size_t size_a, T* b, size_t size_b, Y callback) {
+  const T* probe = a;
+  const T* hay = b;
+  size_t np = size_a, nh = size_b;
+  if (size_a > size_b) {
+    probe = b;
+    hay = a;
+    np = size_b;
+    nh = size_a;
+  }
+  size_t mine = 0;
+  if (nh)
+    for (size_t i = threadIdx.x; i < np; i += blockDim.x) {
+      const T key = probe[i];
+      if (sorted_contains(hay, nh, key)) {
+        ++mine;
+        callback(key);
+      }
+    }
+  return block_reduce(mine);
+}
+
 // Most-frequent-label counter of the CDLP app (dev_utils.h:384-470): an exact
 // open-addressing table in the CTA's 32 KB scratch (one probe; a busy slot sends
 // the label to a count-min sketch that only gives an upper bound), and an exact
@@ -1253,8 +1385,10 @@ class ParallelEngine {
   unsigned BlockGrid(size_t items) const {
     return (unsigned) std::max<size_t>(1, std::min<size_t>(items, (size_t) sms_ * 8));
   }
-  unsigned SharedGrid(size_t ctas_wanted) const {   // 32 KB static shared memory per CTA: 6 CTAs per SM
-    return (unsigned) std::max<size_t>(1, std::min<size_t>(ctas_wanted, (size_t) sms_ * 6));
+  unsigned SharedGrid(size_t ctas_wanted) const {
+    // the *Shared forms keep the reference's bound of 256 CTAs (launcher.h:47-53): apps size
+    // per-CTA global scratch with that constant (lcc_opt.h:189-195)
+    return (unsigned) std::max<size_t>(1, std::min<size_t>(ctas_wanted, 256));
   }
   unsigned long long* Ticket() {
     if (!ticket_) CHECK_CUDA(cudaMalloc(&ticket_, sizeof(unsigned long long)));

@@ -24,6 +24,8 @@
 #include "cuda/app_config.h"
 #include "cuda/bfs/bfs.h"
 #include "cuda/cdlp/cdlp.h"
+#include "cuda/lcc/lcc_opt.h"
+#include "cuda/lcc/lcc_preprocess.h"
 #include "cuda/pagerank/pagerank.h"
 #include "cuda/sssp/sssp.h"
 #include "cuda/wcc/wcc.h"
@@ -40,6 +42,52 @@ int CreateAndQuery(const grape::CommSpec& comm_spec, const std::map<std::string,
   auto t0 = std::chrono::steady_clock::now();
   std::shared_ptr<FRAG_T> fragment = grape::LoadGraph<FRAG_T>(o.at("efile"), o.at("vfile"), comm_spec, graph_spec);
   double load_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  using AppType = APP_T<FRAG_T>;
+  auto app = std::make_shared<AppType>();
+  auto worker = AppType::CreateWorker(app, fragment);
+  worker->Init(comm_spec, app_config, args...);
+  auto q0 = std::chrono::steady_clock::now();
+  worker->Query();
+  double query_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - q0).count();
+  if (!o.at("out_prefix").empty()) {
+    mkdir(o.at("out_prefix").c_str(), 0777);
+    std::ofstream os(grape::GetResultFilename(o.at("out_prefix"), fragment->fid()));
+    worker->Output(os);
+  }
+  worker->Finalize();
+  printf("{\"app\": \"%s\", \"lb\": \"%s\", \"load_s\": %.3f, \"query_ms\": %.4f, \"supersteps\": %d}\n",
+         o.at("application").c_str(), o.at("lb").c_str(), load_s, query_ms, worker->supersteps());
+  return 0;
+}
+
+
+// CreateAndQueryWithPreprocess (run_cuda_app.h:139-183): a CPU app (PRE_T, the
+// reference's own ParallelEngine / ParallelMessageManager) prepares host arrays
+// that the GPU app's context takes as extra Init arguments.
+template <typename EDATA_T, grape::LoadStrategy LS, template <class> class APP_T, template <class> class PRE_T,
+          typename... Args>
+int CreateAndQueryWithPreprocess(const grape::CommSpec& comm_spec, const std::map<std::string, std::string>& o,
+                                 const gc::AppConfig& app_config, Args... args) {
+  using FRAG_T = gc::HostFragment<int64_t, uint32_t, grape::EmptyType, EDATA_T, LS>;
+  grape::LoadGraphSpec graph_spec = grape::DefaultLoadGraphSpec();
+  graph_spec.set_directed(o.at("directed") == "1");
+  graph_spec.set_rebalance(false, 0);
+  auto t0 = std::chrono::steady_clock::now();
+  std::shared_ptr<FRAG_T> fragment = grape::LoadGraph<FRAG_T>(o.at("efile"), o.at("vfile"), comm_spec, graph_spec);
+  double load_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  {
+    // DoPreprocess (run_cuda_app.h:78-106)
+    auto pre = std::make_shared<PRE_T<FRAG_T>>();
+    auto spec = grape::MultiProcessSpec(comm_spec, false);
+    auto worker = PRE_T<FRAG_T>::CreateWorker(pre, fragment);
+    worker->Init(comm_spec, spec);
+    MPI_Barrier(comm_spec.comm());
+    worker->Query(app_config, args...);   // LCCPContext::Init(messages, app_config, sorted_col, row_offset)
+    MPI_Barrier(comm_spec.comm());
+    std::ofstream none;
+    worker->Output(none);
+    worker->Finalize();
+  }
   using AppType = APP_T<FRAG_T>;
   auto app = std::make_shared<AppType>();
   auto worker = AppType::CreateWorker(app, fragment);
@@ -103,6 +151,12 @@ int main(int argc, char** argv) {
         rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kBothOutIn, gc::Pagerank>(comm_spec, o, app_config, std::stod(o["pr_d"]), std::stoi(o["pr_mr"]));
       else
         rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kOnlyOut, gc::Pagerank>(comm_spec, o, app_config, (float) std::stod(o["pr_d"]), std::stoi(o["pr_mr"]));
+    } else if (a == "lcc" && !directed) {
+      // run_cuda_app.h:287-303 (undirected: LCCOPT + the CPU preprocess LCCP)
+      uint32_t** col = reinterpret_cast<uint32_t**>(malloc(sizeof(uint32_t*)));
+      size_t** row_offset = reinterpret_cast<size_t**>(malloc(sizeof(size_t*)));
+      rc = CreateAndQueryWithPreprocess<grape::EmptyType, LoadStrategy::kOnlyOut, gc::LCCOPT, grape::LCCP>(
+          comm_spec, o, app_config, col, row_offset);
     } else if (a == "cdlp") {
       if (directed)
         rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kBothOutIn, gc::CDLP>(comm_spec, o, app_config, std::stoi(o["cdlp_mr"]));

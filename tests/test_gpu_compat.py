@@ -99,3 +99,13 @@ def test_cdlp_exact(dataset, lb):
     headers reproduces the golden labels (misc/cuda_app_tests.sh: ExactVerify p2p-31-CDLP)."""
     info, text = run(dataset, "cdlp", lb, cdlp_mr=10)
     assert text == G.golden_lines("p2p-31-CDLP")
+
+
+@pytest.mark.parametrize("lb", ["cm"])
+def test_lcc_exact(dataset, lb):
+    """The reference's UNCHANGED cuda/lcc/lcc_opt.h + its CPU preprocess lcc_preprocess.h (the
+    reference's own ParallelEngine / ParallelMessageManager) on the compat headers: ShmHashTable,
+    intersect_num{,_blk}, ForEachWithIndexWarp{Shared,Dynamic} / BlockDynamic
+    (misc/cuda_app_tests.sh:114-115: ExactVerify p2p-31-LCC)."""
+    info, text = run(dataset, "lcc", lb)
+    assert text == G.golden_lines("p2p-31-LCC")
