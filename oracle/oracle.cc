@@ -10,7 +10,8 @@
 // golden vectors dataset/p2p-31-{BFS,BFS-directed,SSSP,SSSP-directed,PR,
 // PR-directed,CDLP,LCC,WCC} (tests/test_oracle_golden.py, comparison rules of
 // misc/app_tests.sh:6-40), and -- when oracle/_ref is built -- against the
-// unmodified reference CPU apps on RMAT graphs (tests/test_oracle_vs_ref.py).
+// unmodified reference CPU apps on R-MAT graphs and on randomised multigraphs
+// (tests/test_ref_golden.py).
 //
 // Citations are to files under /root/reference.
 //
