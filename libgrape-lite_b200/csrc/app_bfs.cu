@@ -917,6 +917,10 @@ struct BfsApp : gl_app {
   const uint64_t* g_rp = nullptr;
   const uint32_t* g_col = nullptr;
   const uint32_t* g_nz = nullptr;
+  // adjacency the pull step scans (== g_* unless the fragment is directed)
+  const uint64_t* p_rp = nullptr;
+  const uint32_t* p_col = nullptr;
+  uint32_t* nz_in = nullptr;   // directed: inner vertices with in-degree > 0
   uint32_t *perm = nullptr, *order = nullptr, *nz_p = nullptr, *col_p = nullptr;
   uint64_t* rp_p = nullptr;
   uint32_t src_ = 0;
@@ -949,17 +953,20 @@ struct BfsApp : gl_app {
     cudaFree(nz_p);
     cudaFree(col_p);
     cudaFree(rp_p);
+    cudaFree(nz_in);
   }
   size_t ResultElemBytes() const override { return sizeof(int64_t); }
 
   uint32_t* level_bm(uint32_t d) { return lv + (size_t) d * words; }
   // pull scans whole rows: with several fragments the frontier bits of the
   // outer copies are refreshed from their owners first (mirror sync)
-  const uint64_t* row_end() const { return g_rp + 1; }
+  const uint64_t* row_end() const { return p_rp + 1; }
 
-  // directed graphs: the pull step would need the incoming adjacency
-  // (bfs.h:225-238); levels are identical with push only.
-  bool can_pull() const { return cfg.direction_opt && !(fv.directed && !frag->ie_alias_oe); }
+  // The pull step walks the INCOMING adjacency (bfs.h:225-238): `ie` when the
+  // fragment is directed, the (aliased) `oe` when it is not.  A directed
+  // fragment that was created without an ie CSR (gl_frag_create, kOnlyOut)
+  // can only push; levels are identical either way.
+  bool can_pull() const { return cfg.direction_opt && (!fv.directed || !frag->ie_alias_oe); }
 
   int Setup() override {
     tvnum = fv.ivnum + fv.ovnum;
@@ -982,7 +989,7 @@ struct BfsApp : gl_app {
     g_col = fv.oe_col;
     g_nz = frag->nonzero_deg;
     // hub-first shadow graph (one fragment, undirected, large enough to matter)
-    if (fv.fnum == 1 && can_pull() && fv.ivnum >= (1u << 16) && cfg.reserved[1] == 0) {
+    if (fv.fnum == 1 && can_pull() && !fv.directed && fv.ivnum >= (1u << 16) && cfg.reserved[1] == 0) {
       GL_TRY(build_hub_order(eng.stream, fv.oe_rp, fv.ivnum, &perm, &order));
       GL_TRY(build_permuted_csr(eng.stream, fv.oe_rp, fv.oe_col, frag->oe.entries, fv.ivnum, order, perm, &rp_p, &col_p));
       GL_CUDA(cudaMalloc(&nz_p, sizeof(uint32_t) * words));
@@ -992,8 +999,18 @@ struct BfsApp : gl_app {
       g_col = col_p;
       g_nz = nz_p;
     }
+    p_rp = g_rp;
+    p_col = g_col;
+    if (fv.directed && can_pull()) {
+      p_rp = fv.ie_rp;
+      p_col = fv.ie_col;
+      GL_CUDA(cudaMalloc(&nz_in, sizeof(uint32_t) * words));
+      GL_CUDA(cudaMemsetAsync(nz_in, 0, sizeof(uint32_t) * words, eng.stream));
+      if (fv.ivnum) GL_LAUNCH(k_bfs_nz, (fv.ivnum + 255) / 256, 256, eng.stream, p_rp, fv.ivnum, nz_in);
+      g_nz = nz_in;   // pull candidates / "still reachable" statistics: in-degree > 0
+    }
     if (fv.ivnum && can_pull())
-      GL_LAUNCH(k_bfs_hub_nbr, eng.sm_count * 8, 256, eng.stream, g_rp, row_end(), g_col, fv.ivnum, hub_nbr);
+      GL_LAUNCH(k_bfs_hub_nbr, eng.sm_count * 8, 256, eng.stream, p_rp, row_end(), p_col, fv.ivnum, hub_nbr);
     {
       unsigned long long* d_cnt = nullptr;
       GL_CUDA(cudaMalloc(&d_cnt, 8));
@@ -1069,7 +1086,7 @@ struct BfsApp : gl_app {
   }
 
   PullArgs pull_args() const {
-    return PullArgs{g_rp, row_end(), g_col, hub_nbr, fv.ivnum, g_nz};
+    return PullArgs{p_rp, row_end(), p_col, hub_nbr, fv.ivnum, g_nz};
   }
 
   bool fused() const {

@@ -162,6 +162,10 @@ struct PageRankApp : gl_app {
   size_t words = 0;
   uint32_t tvnum = 0;
   int curr_iter = 0;
+  // The pull sweep gathers along oe rows, which are the IN-neighbours only when
+  // the fragment is undirected; on a directed fragment pr_pull falls back to the
+  // push formulation (same ranks, pagerank.h:207-221), never a wrong gather.
+  bool use_pull() const { return cfg.pr_pull && !fv.directed; }
 
   ~PageRankApp() override {
     cudaFree(rank);
@@ -182,12 +186,12 @@ struct PageRankApp : gl_app {
     GL_CUDA(cudaMalloc(&d_dangling, sizeof(double)));
     GL_CUDA(cudaMalloc(&all_inner, sizeof(uint32_t) * words));
     GL_LAUNCH(k_ones, (unsigned) ((words + 255) / 256), 256, eng.stream, all_inner, fv.ivnum, (uint32_t) words);
-    if (cfg.pr_pull) {
+    if (use_pull()) {
       GL_CUDA(cudaMalloc(&contrib, sizeof(double) * std::max<uint32_t>(tvnum, 1)));
       if (fv.fnum == 1 && fv.ivnum) GL_TRY(BuildHubOrder());
     }
     GL_TRY(mm.Init(comm, fv, sizeof(ItemU32F64)));
-    if (cfg.pr_pull && fv.fnum > 1) GL_TRY(mm.BuildMirrorPlan(eng.stream, fv));
+    if (use_pull() && fv.fnum > 1) GL_TRY(mm.BuildMirrorPlan(eng.stream, fv));
     return GL_OK;
   }
 
@@ -274,7 +278,7 @@ struct PageRankApp : gl_app {
     GL_TRY(mm.AllReduceF64(&dangling, 1, 0));
     const double N = (double) fv.total_vnum;
     const double base = (1.0 - cfg.pr_delta) / N + cfg.pr_delta * dangling / N;
-    if (cfg.pr_pull) {
+    if (use_pull()) {
       if (cfg.reserved[5] == 1) GL_TRY(pull_sweep<float>(s, base));
       else GL_TRY(pull_sweep<double>(s, base));
     } else {

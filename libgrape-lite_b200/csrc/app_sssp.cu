@@ -80,12 +80,20 @@ __global__ void k_sssp_seed(uint32_t src, T* dist, uint32_t* in_q) {
 
 template <typename WT>
 __global__ void k_weight_sum(const WT* w, uint64_t m, double* out) {
+  // out[0] += sum of the weights; out[1] = 1 when a weight is negative, -0.0 or
+  // NaN: the device atomic-min orders distances by their bit patterns
+  // (common.cuh atomic_min_*_nonneg), which is only an order for values >= +0
   double s = 0;
+  bool bad = false;
   for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < m;
-       i += (uint64_t) gridDim.x * blockDim.x)
-    s += (double) w[i];
+       i += (uint64_t) gridDim.x * blockDim.x) {
+    const WT x = w[i];
+    s += (double) x;
+    bad |= !(x >= (WT) 0) || signbit(x);
+  }
   s = warp_sum(s);
   if (lane_id() == 0) atomicAdd(out, s);
+  if (bad) out[1] = 1.0;
 }
 
 template <typename T>
@@ -159,24 +167,30 @@ struct SsspApp : gl_app {
     GL_CUDA(cudaMalloc(&out64, sizeof(double) * std::max<uint32_t>(fv.ivnum, 1)));
     // init_prio heuristic (sssp.h:76-92)
     double p = cfg.sssp_prio;
-    if (p <= 0) {
+    {
       double wsum = (double) frag->oe.entries;  // unweighted: every edge counts 1
       if (frag->oe.w && frag->oe.entries) {
         double* d_sum;
-        GL_CUDA(cudaMalloc(&d_sum, 8));
-        GL_CUDA(cudaMemsetAsync(d_sum, 0, 8, eng.stream));
+        double h_sum[2] = {0, 0};
+        GL_CUDA(cudaMalloc(&d_sum, 16));
+        GL_CUDA(cudaMemsetAsync(d_sum, 0, 16, eng.stream));
         if (fv.edata_bytes == 4) {
           GL_LAUNCH(k_weight_sum<float>, eng.sm_count * 8, 256, eng.stream, (const float*) frag->oe.w, frag->oe.entries, d_sum);
         } else {
           GL_LAUNCH(k_weight_sum<double>, eng.sm_count * 8, 256, eng.stream, (const double*) frag->oe.w, frag->oe.entries, d_sum);
         }
-        GL_CUDA(cudaMemcpyAsync(&wsum, d_sum, 8, cudaMemcpyDeviceToHost, eng.stream));
+        GL_CUDA(cudaMemcpyAsync(h_sum, d_sum, 16, cudaMemcpyDeviceToHost, eng.stream));
         GL_CUDA(cudaStreamSynchronize(eng.stream));
         cudaFree(d_sum);
+        wsum = h_sum[0];
+        if (h_sum[1] != 0.0) {
+          set_error("SSSP: negative (or -0.0 / NaN) edge weights are not supported");
+          return GL_ERR_ARG;
+        }
       }
       double m = (double) std::max<uint64_t>(frag->oe.entries, 1);
       double iv = (double) std::max<uint32_t>(fv.ivnum, 1);
-      p = 32.0 * (wsum / m) / (m / iv);
+      if (p <= 0) p = 32.0 * (wsum / m) / (m / iv);
     }
     init_prio = (T) p;
     return mm.Init(comm, fv, sizeof(ItemDist<T>));

@@ -131,6 +131,12 @@ struct WccApp : gl_app {
   size_t ResultElemBytes() const override { return sizeof(int64_t); }
 
   int Setup() override {
+    // weak connectivity needs both edge directions (wcc.h:181-197 scans ie and oe):
+    // a directed fragment created without an ie CSR cannot provide them
+    if (fv.directed && frag->ie_alias_oe) {
+      set_error("WCC on a directed fragment needs the incoming adjacency (gl_frag_desc.ie / kBothOutIn)");
+      return GL_ERR_ARG;
+    }
     tvnum = fv.ivnum + fv.ovnum;
     words = bm_words(tvnum) + 1;
     GL_CUDA(cudaMalloc(&label, sizeof(uint32_t) * std::max<uint32_t>(tvnum, 1)));

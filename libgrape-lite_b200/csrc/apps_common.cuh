@@ -161,7 +161,8 @@ k_unpack(MsgView mv, Apply apply, ScanCtrl* ctrl) {
   ScanAcc acc;
   for (uint32_t src = 0; src < mv.fnum; ++src) {
     if (src == mv.fid) continue;
-    const uint32_t n = mv.recv_count[src];
+    uint32_t n = mv.recv_count[src];
+    if (n > mv.capacity) n = mv.capacity;   // an overflowing producer dropped the rest (FinishARound reports it)
     const Item* items = (const Item*) mv.recv_slot[src];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += gridDim.x * blockDim.x)

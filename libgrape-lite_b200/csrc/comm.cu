@@ -75,7 +75,21 @@ __global__ void k_peer_allreduce(uint32_t fnum, uint32_t fid, PeerSlot* const* m
     *(volatile unsigned long long*) &dst->tag = tag;
     // wait for peer p's contribution in MY header, slot [p]
     const volatile PeerSlot* src = local_slots + p;
-    while (src->tag != tag) __nanosleep(64);
+    // bounded wait: a peer that failed on the host never arrives; report it
+    // instead of spinning forever inside a kernel (GL_ERR_COMM on the host)
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    bool late = false;
+    while (src->tag != tag) {
+      __nanosleep(64);
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) {   // 20 s
+        late = true;
+        break;
+      }
+    }
+    if (late) atomicExch(&s_total, 0xFFFFFFFFu);
     __threadfence_system();
     s_i0[p] = src->i0;
     s_i1[p] = src->i1;
@@ -99,7 +113,7 @@ __global__ void k_peer_allreduce(uint32_t fnum, uint32_t fid, PeerSlot* const* m
     h_out->i2 = e2;
     h_out->i3 = e3;
     h_out->d0 = c;
-    h_out->tag = tag;
+    h_out->tag = (s_total == 0xFFFFFFFFu) ? ~0ull : tag;   // ~0: a peer timed out
   }
   (void) fid;
 }
@@ -423,6 +437,10 @@ int MessageManager::PeerAllReduce(cudaStream_t s, long long* i0, long long* i1, 
   GL_COUNT_LAUNCH();
   GL_CUDA(cudaGetLastError());
   GL_CUDA(cudaStreamSynchronize(s));
+  if (h_result->tag == ~0ull) {
+    set_error("peer collective timed out (a fragment of the group did not arrive)");
+    return GL_ERR_COMM;
+  }
   *i0 = h_result->i0;
   *i1 = h_result->i1;
   *d0 = h_result->d0;
@@ -553,6 +571,10 @@ int MessageManager::FinishARound(cudaStream_t s) {
       GL_COUNT_LAUNCH();
       GL_CUDA(cudaGetLastError());
       GL_CUDA(cudaStreamSynchronize(s));
+      if (h_result->tag == ~0ull) {
+        set_error("round barrier timed out (a fragment of the group did not arrive)");
+        return GL_ERR_COMM;
+      }
       vote[0] = h_result->i0;
       vote[1] = h_result->i1;
       stat_out[0] = h_result->i2;

@@ -18,8 +18,18 @@ def main():
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    # GL_ONE_DEVICE=1: every rank's fragment lives on cuda:0 (the contexts of the
+    # rank processes time-slice one GPU; CUDA IPC maps the landing areas across
+    # them) -- the multi-fragment data plane on a 1-GPU box.  Rendezvous: gloo.
+    one_dev = os.environ.get("GL_ONE_DEVICE", "0") == "1"
+    if one_dev:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if one_dev:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = "cpu" if one_dev else "cuda"
     pkg = importlib.import_module("libgrape-lite_b200")
     gdist = importlib.import_module("libgrape-lite_b200.dist")
     from oracle import pyoracle
@@ -41,9 +51,12 @@ def main():
             source = g.max_degree_vertex()
         else:
             source = 0
-        src_t = torch.tensor([source], dtype=torch.int64, device="cuda")
+        src_t = torch.tensor([source], dtype=torch.int64, device=dev)
         dist.broadcast(src_t, 0)
         source = int(src_t.item())
+        only = os.environ.get("GL_APPS")
+        if only:
+            apps = [a for a in apps if a in only.split(",")]
         for name in apps:
             cfg = {}
             kind = name
@@ -85,7 +98,7 @@ def main():
             dist.barrier()
         comm.close()
         frag.close()
-    flag = torch.tensor([len(failures)], device="cuda")
+    flag = torch.tensor([len(failures)], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
     sys.exit(1 if int(flag.item()) else 0)

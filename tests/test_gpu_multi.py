@@ -1,5 +1,13 @@
-"""GPU, >= 2 devices: edge-cut multi-fragment parity through the NVLink
-peer-memory message manager (one process per GPU, launched with torchrun)."""
+"""Edge-cut multi-fragment parity through the peer-memory message manager
+(csrc/comm.cu): one process per fragment, launched with torchrun.
+
+* test_multi_fragment_one_device: every rank's fragment lives on cuda:0 (the
+  rank processes' contexts time-slice the GPU, CUDA IPC maps the landing areas
+  across them).  Runs on a 1-GPU box and exercises the whole data plane --
+  msg_send / pack_outer_phase / k_unpack, the device-side round barrier and
+  vote, the dense mirror sync, the fused multi-fragment BFS kernel with its
+  in-kernel collectives -- for all six apps at 2 and 3 fragments.
+* test_multi_fragment_parity: one fragment per GPU over NVLink (>= 2 devices)."""
 import os
 import subprocess
 import sys
@@ -28,3 +36,17 @@ def test_multi_fragment_parity(nproc):
     p = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     sys.stdout.write(p.stdout[-4000:])
     assert p.returncode == 0, p.stdout[-4000:]
+
+
+@pytest.mark.parametrize("nproc,scale", [(2, 12), (3, 11)])
+def test_multi_fragment_one_device(nproc, scale):
+    if _ngpus() < 1:
+        pytest.skip("needs a GPU")
+    env = dict(os.environ, GL_ONE_DEVICE="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(29520 + nproc),
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), str(scale)]
+    p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    sys.stdout.write(p.stdout[-4000:])
+    assert p.returncode == 0, p.stdout[-4000:]
+    assert p.stdout.count(" OK") >= 11, p.stdout[-4000:]
