@@ -900,6 +900,14 @@ class DeviceFragment {
 };
 }  // namespace dev
 
+inline int b200_pick_device(int local_id) {
+  // run_cuda_app.h:207-214 binds rank i to device i; with more ranks than
+  // devices (several fragments time-slicing one GPU) ranks wrap around
+  int n = 0;
+  CHECK_CUDA(cudaGetDeviceCount(&n));
+  return n > 0 ? local_id % n : 0;
+}
+
 // ------------------------------------------------------------ host fragment --
 // grape/cuda/fragment/host_fragment.h:66-660: the CPU fragment of the
 // reference + a device-resident SoA copy owned by the C-ABI library.
@@ -936,14 +944,14 @@ class HostFragment
   void Init(const CommSpec& comm_spec, bool directed, std::unique_ptr<VertexMap<OID_T, VID_T>>&& vm_ptr,
             std::vector<internal_vertex_t>& vertices, std::vector<edge_t>& edges) {
     base_t::Init(comm_spec, directed, std::move(vm_ptr), vertices, edges);
-    Upload(comm_spec.local_id());
+    Upload(b200_pick_device(comm_spec.local_id()));
   }
 
   template <typename IOADAPTOR_T>
   void Deserialize(const CommSpec& comm_spec, std::unique_ptr<VertexMap<OID_T, VID_T>>&& vm_ptr,
                    const std::string& prefix) {
     base_t::template Deserialize<IOADAPTOR_T>(comm_spec, std::move(vm_ptr), prefix);
-    Upload(comm_spec.local_id());
+    Upload(b200_pick_device(comm_spec.local_id()));
   }
 
   void PrepareToRunApp(const CommSpec& comm_spec, PrepareConf conf, const ParallelEngineSpec& pe_spec) {
@@ -1030,85 +1038,380 @@ class HostFragment
 };
 
 // ---------------------------------------------------------- message manager --
-// grape/cuda/parallel/gpu_message_manager.h:45-458.  One fragment per process
-// in this round: no message ever leaves the fragment, rounds still follow the
-// reference's protocol (ForceContinue / ToTerminate).
+// grape/cuda/parallel/gpu_message_manager.h:45-458 on the C ABI's gl_mm_*
+// (include/grape_b200.h): the InArchive a producer appends to IS the
+// destination fragment's landing slot, mapped over NVLink / CUDA IPC -- the
+// store is the transfer.  No staging archive, no ncclSend/ncclRecv, no host
+// MPI_Allgather of sizes; FinishARound = one device-side barrier + vote.
+
 namespace dev {
+// dev::OutArchive (serialization/out_archive.h:32-89): what one source fragment
+// sent me in the previous round
+class OutArchive {
+ public:
+  OutArchive() = default;
+  DEV_HOST_INLINE OutArchive(const char* data, uint32_t size) : data_(data), size_(size) {}
+  DEV_HOST_INLINE uint32_t size() const { return size_; }
+  DEV_HOST_INLINE const char* data() const { return data_; }
+  DEV_HOST_INLINE bool Empty() const { return size_ == 0; }
+
+ private:
+  const char* data_ = nullptr;
+  uint32_t size_ = 0;
+};
+
+// dev::InArchive (serialization/in_archive.h:36-103): append-only byte buffer
+// of ONE destination fragment
+class InArchive {
+ public:
+  InArchive() = default;
+  DEV_HOST_INLINE InArchive(char* slot, uint32_t* bytes, uint32_t cap) : slot_(slot), bytes_(bytes), cap_(cap) {}
+  template <typename T>
+  DEV_INLINE void AddBytes(const T& elem) {
+    const uint32_t off = atomicAdd(bytes_, (uint32_t) sizeof(T));
+    if (off + sizeof(T) <= cap_) *reinterpret_cast<T*>(slot_ + off) = elem;
+  }
+  // one reservation per warp (all active lanes append to THIS archive)
+  template <typename T>
+  DEV_INLINE void AddBytesWarp(const T& elem) {
+    const uint32_t active = __activemask();
+    const uint32_t leader = __ffs(active) - 1;
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == leader) base = atomicAdd(bytes_, (uint32_t) (__popc(active) * sizeof(T)));
+    base = __shfl_sync(active, base, leader);
+    const uint32_t off = base + __popc(active & ((1u << (threadIdx.x & 31)) - 1)) * (uint32_t) sizeof(T);
+    if (off + sizeof(T) <= cap_) *reinterpret_cast<T*>(slot_ + off) = elem;
+  }
+
+ private:
+  char* slot_ = nullptr;
+  uint32_t* bytes_ = nullptr;
+  uint32_t cap_ = 0;
+};
+
 class MessageManager {
  public:
+  MessageManager() { memset(&mv_, 0, sizeof(mv_)); }
+  explicit MessageManager(const gl_mm_view& mv) : mv_(mv) {}
+
+  // (gid of the outer vertex, msg) to the vertex's owner (:53-82)
   template <typename GRAPH_T, typename MESSAGE_T>
-  DEV_INLINE void SyncStateOnOuterVertex(const GRAPH_T&, const typename GRAPH_T::vertex_t&, const MESSAGE_T&) {
-    assert(false && "single-fragment build: no outer vertices");
+  DEV_INLINE void SyncStateOnOuterVertex(const GRAPH_T& frag, const typename GRAPH_T::vertex_t& v,
+                                         const MESSAGE_T& msg) {
+    archive(frag.GetFragId(v)).AddBytes(thrust::make_pair(frag.GetOuterVertexGid(v), msg));
   }
   template <typename GRAPH_T>
-  DEV_INLINE void SyncStateOnOuterVertex(const GRAPH_T&, const typename GRAPH_T::vertex_t&) {
-    assert(false && "single-fragment build: no outer vertices");
+  DEV_INLINE void SyncStateOnOuterVertex(const GRAPH_T& frag, const typename GRAPH_T::vertex_t& v) {
+    archive(frag.GetFragId(v)).AddBytes(frag.GetOuterVertexGid(v));
   }
+  // lanes of a warp that target the same owner share one reservation
+  // (in_archive.h:52-67 AddBytesWarpOpt)
   template <typename GRAPH_T, typename MESSAGE_T>
-  DEV_INLINE void SyncStateOnOuterVertexWarpOpt(const GRAPH_T&, const typename GRAPH_T::vertex_t&, const MESSAGE_T&) {
-    assert(false && "single-fragment build: no outer vertices");
+  DEV_INLINE void SyncStateOnOuterVertexWarpOpt(const GRAPH_T& frag, const typename GRAPH_T::vertex_t& v,
+                                                const MESSAGE_T& msg) {
+    warp_opt(frag.GetFragId(v), thrust::make_pair(frag.GetOuterVertexGid(v), msg));
   }
   template <typename GRAPH_T>
-  DEV_INLINE void SyncStateOnOuterVertexWarpOpt(const GRAPH_T&, const typename GRAPH_T::vertex_t&) {
-    assert(false && "single-fragment build: no outer vertices");
+  DEV_INLINE void SyncStateOnOuterVertexWarpOpt(const GRAPH_T& frag, const typename GRAPH_T::vertex_t& v) {
+    warp_opt(frag.GetFragId(v), frag.GetOuterVertexGid(v));
+  }
+  // (gid of the inner vertex, msg) to every fragment that holds a copy reachable
+  // through in / out / both edge sets (:84-139; DestList = IEDests/OEDests/IOEDests)
+  template <typename GRAPH_T, typename MESSAGE_T>
+  DEV_INLINE void SendMsgThroughIEdges(const GRAPH_T& frag, const typename GRAPH_T::vertex_t& v,
+                                       const MESSAGE_T& msg) {
+    through(frag, v, 2, thrust::make_pair(frag.GetInnerVertexGid(v), msg));
   }
   template <typename GRAPH_T, typename MESSAGE_T>
-  DEV_INLINE void SendMsgThroughOEdges(const GRAPH_T&, const typename GRAPH_T::vertex_t&, const MESSAGE_T&) {}
+  DEV_INLINE void SendMsgThroughOEdges(const GRAPH_T& frag, const typename GRAPH_T::vertex_t& v,
+                                       const MESSAGE_T& msg) {
+    through(frag, v, 1, thrust::make_pair(frag.GetInnerVertexGid(v), msg));
+  }
+  template <typename GRAPH_T>
+  DEV_INLINE void SendMsgThroughOEdges(const GRAPH_T& frag, const typename GRAPH_T::vertex_t& v) {
+    through(frag, v, 1, frag.GetInnerVertexGid(v));
+  }
   template <typename GRAPH_T, typename MESSAGE_T>
-  DEV_INLINE void SendMsgThroughEdges(const GRAPH_T&, const typename GRAPH_T::vertex_t&, const MESSAGE_T&) {}
+  DEV_INLINE void SendMsgThroughEdges(const GRAPH_T& frag, const typename GRAPH_T::vertex_t& v,
+                                      const MESSAGE_T& msg) {
+    through(frag, v, 3, thrust::make_pair(frag.GetInnerVertexGid(v), msg));
+  }
+  template <typename MESSAGE_T>
+  DEV_INLINE void SendToFragment(fid_t dst_fid, const MESSAGE_T& msg) {
+    archive(dst_fid).AddBytes(msg);
+  }
+  template <typename MESSAGE_T>
+  DEV_INLINE void SendToFragmentWarpOpt(fid_t dst_fid, const MESSAGE_T& msg) {
+    warp_opt(dst_fid, msg);
+  }
+  DEV_HOST_INLINE const gl_mm_view& view() const { return mv_; }
+
+ private:
+  DEV_INLINE InArchive archive(fid_t f) const {
+    return InArchive(mv_.send_slot[f], mv_.send_bytes + f, mv_.capacity_bytes);
+  }
+  template <typename T>
+  DEV_INLINE void warp_opt(fid_t f, const T& item) const {
+    const uint32_t active = __activemask();
+    const uint32_t peers = __match_any_sync(active, f);
+    const uint32_t leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == leader) base = atomicAdd(mv_.send_bytes + f, (uint32_t) (__popc(peers) * sizeof(T)));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t off = base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1)) * (uint32_t) sizeof(T);
+    if (off + sizeof(T) <= mv_.capacity_bytes) *reinterpret_cast<T*>(mv_.send_slot[f] + off) = item;
+  }
+  // Destination fragments of v = owners of the outer neighbours in the chosen
+  // edge sets.  The outer part of a row ([split, end)) is sorted by gid, i.e.
+  // grouped by owner, so the owner set is read off the row itself -- the
+  // reference precomputes the same set as fid lists (idst_/odst_/iodst_,
+  // immutable_edgecut_fragment.h:606-722).  fnum <= 64: a 64-bit set.
+  template <typename GRAPH_T, typename T>
+  DEV_INLINE void through(const GRAPH_T& frag, const typename GRAPH_T::vertex_t& v, int which, const T& item) const {
+    const gl_frag_view& fv = frag.view();
+    const uint32_t u = v.GetValue();
+    unsigned long long set = 0;
+    if (which & 1)
+      for (uint64_t p = fv.oe_split[u]; p < fv.oe_rp[u + 1]; ++p)
+        set |= 1ull << (fv.ovgid[fv.oe_col[p] - fv.ivnum] >> fv.fid_offset);
+    if ((which & 2) && !((which & 1) && fv.ie_col == fv.oe_col))
+      for (uint64_t p = fv.ie_split[u]; p < fv.ie_rp[u + 1]; ++p)
+        set |= 1ull << (fv.ovgid[fv.ie_col[p] - fv.ivnum] >> fv.fid_offset);
+    while (set) {
+      const fid_t f = (fid_t) (__ffsll((long long) set) - 1);
+      set &= set - 1;
+      archive(f).AddBytes(item);
+    }
+  }
+  gl_mm_view mv_;
 };
+
+// message_kernels.h:28-127 ProcessMsg: apply func to every received unit
+template <typename GRAPH_T, typename MESSAGE_T, typename FUNC_T>
+__global__ void ProcessMsg(gl_mm_view mv, const GRAPH_T frag, FUNC_T func) {
+  using vid_t = typename GRAPH_T::vid_t;
+  for (fid_t src = 0; src < mv.fnum; ++src) {
+    if (src == mv.fid) continue;
+    uint32_t bytes = mv.recv_bytes[src];
+    if (bytes > mv.capacity_bytes) bytes = mv.capacity_bytes;
+    if constexpr (std::is_same<MESSAGE_T, grape::EmptyType>::value) {
+      const vid_t* units = reinterpret_cast<const vid_t*>(mv.recv_slot[src]);
+      const size_t n = bytes / sizeof(vid_t);
+      for (size_t i = TID_1D; i < n; i += TOTAL_THREADS_1D) {
+        typename GRAPH_T::vertex_t v;
+        bool ok = frag.Gid2Vertex(units[i], v);
+        assert(ok);
+        (void) ok;
+        func(v);
+      }
+    } else {
+      using unit_t = thrust::pair<vid_t, MESSAGE_T>;
+      const unit_t* units = reinterpret_cast<const unit_t*>(mv.recv_slot[src]);
+      const size_t n = bytes / sizeof(unit_t);
+      for (size_t i = TID_1D; i < n; i += TOTAL_THREADS_1D) {
+        const unit_t unit = units[i];
+        typename GRAPH_T::vertex_t v;
+        bool ok = frag.Gid2Vertex(unit.first, v);
+        assert(ok);
+        (void) ok;
+        func(v, unit.second);
+      }
+    }
+  }
+}
+template <typename MESSAGE_T, typename FUNC_T>
+__global__ void ProcessRawMsg(gl_mm_view mv, FUNC_T func) {
+  for (fid_t src = 0; src < mv.fnum; ++src) {
+    if (src == mv.fid) continue;
+    uint32_t bytes = mv.recv_bytes[src];
+    if (bytes > mv.capacity_bytes) bytes = mv.capacity_bytes;
+    const MESSAGE_T* units = reinterpret_cast<const MESSAGE_T*>(mv.recv_slot[src]);
+    const size_t n = bytes / sizeof(MESSAGE_T);
+    for (size_t i = TID_1D; i < n; i += TOTAL_THREADS_1D) func(units[i]);
+  }
+}
 }  // namespace dev
 
 class GPUMessageManager {
  public:
   GPUMessageManager() = default;
+  ~GPUMessageManager() { Release(false); }
+  GPUMessageManager(const GPUMessageManager&) = delete;
+  GPUMessageManager& operator=(const GPUMessageManager&) = delete;
+
+  // :160-194.  The NCCL communicator of the reference is replaced by a
+  // fragment-group communicator whose landing areas are mapped at InitBuffer
+  // time (the slot capacity is only known then).
   void Init(const grape::CommSpec& comm_spec) {
-    if (comm_spec.fnum() != 1)
-      LOG(FATAL) << "b200 compat headers: one fragment per process in this build; "
-                    "multi-fragment runs go through gl_app_* (include/grape_b200.h)";
+    comm_spec_ = comm_spec;
+    fnum_ = comm_spec.fnum();
+    fid_ = comm_spec.fid();
+    CHECK_CUDA(cudaSetDevice(b200_pick_device(comm_spec.local_id())));
+    if (fnum_ == 1) CHECK_GL(gl_mm_create(&mm_, nullptr));
   }
-  void InitBuffer(size_t, size_t) {}
-  void DropBuffer() {}
-  void Start() {}
-  void StartARound() { force_continue_ = false; }
+
+  // :196-204.  Collective: every fragment's app context calls it with sizes
+  // derived from its own vertex counts; the group agrees on the largest.
+  void InitBuffer(size_t send_buffer_capacity, size_t recv_buffer_capacity) {
+    if (fnum_ == 1) return;
+    unsigned long long need = std::max(send_buffer_capacity, recv_buffer_capacity) + 256, all = 0;
+    MPI_Allreduce(&need, &all, 1, MPI_UNSIGNED_LONG_LONG, MPI_MAX, comm_spec_.comm());
+    if (mm_ && all <= capacity_) return;
+    Release(true);
+    gl_comm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.fid = fid_;
+    d.fnum = fnum_;
+    d.allreduce = &GPUMessageManager::HostAllReduce;
+    d.user = this;
+    d.landing_bytes = (size_t) all;
+    d.mirror_bytes = 0;
+    CHECK_GL(gl_comm_create(&comm_, &d));
+    std::vector<char> mine(GL_IPC_HANDLE_BYTES), handles((size_t) GL_IPC_HANDLE_BYTES * fnum_);
+    CHECK_GL(gl_comm_export(comm_, mine.data(), mine.size()));
+    MPI_Allgather(mine.data(), GL_IPC_HANDLE_BYTES, MPI_CHAR, handles.data(), GL_IPC_HANDLE_BYTES, MPI_CHAR,
+                  comm_spec_.comm());
+    CHECK_GL(gl_comm_open(comm_, handles.data(), handles.size()));
+    CHECK_GL(gl_mm_create(&mm_, comm_));
+    CHECK_GL(gl_mm_init_buffer(mm_, send_buffer_capacity, recv_buffer_capacity));
+    capacity_ = all;
+    MPI_Barrier(comm_spec_.comm());   // every landing area is mapped before the first round
+  }
+  void DropBuffer() { Release(true); }
+
+  void Start() {
+    if (mm_) CHECK_GL(gl_mm_start(mm_));
+    round_started_ = false;
+  }
+  void StartARound() {
+    EnsureManager();
+    CHECK_GL(gl_mm_start_round(mm_, stream_.cuda_stream()));
+  }
   void FinishARound() {
-    stream_.Sync();
-    terminate_ = !force_continue_;
+    EnsureManager();
+    CHECK_GL(gl_mm_finish_round(mm_, stream_.cuda_stream()));
+    int t = 0;
+    CHECK_GL(gl_mm_to_terminate(mm_, &t));
+    terminate_ = t != 0;
   }
   void Finalize() const {}
   bool ToTerminate() const { return terminate_; }
-  void ForceContinue() { force_continue_ = true; }
-  size_t GetMsgSize() const { return 0; }
+  void ForceContinue() {
+    EnsureManager();
+    CHECK_GL(gl_mm_force_continue(mm_));
+  }
+  size_t GetMsgSize() const { return mm_ ? (size_t) gl_mm_bytes_sent(mm_) : 0; }
   double GetAccumulatedCommTime() const { return 0.0; }
   Stream& stream() { return stream_; }
   void* nccl_comm() { return nullptr; }
-  dev::MessageManager DeviceObject() { return dev::MessageManager(); }
-  template <typename GRAPH_T, typename MESSAGE_T, typename FUNC_T>
-  void ParallelProcess(const GRAPH_T&, FUNC_T) {}   // nothing is ever received at fnum == 1
-  template <typename MESSAGE_T, typename FUNC_T>
-  void ParallelProcess(FUNC_T) {}
+  gl_mm_t* handle() const { return mm_; }
+  dev::MessageManager DeviceObject() {
+    EnsureManager();
+    gl_mm_view mv;
+    CHECK_GL(gl_mm_view_get(mm_, &mv));
+    return dev::MessageManager(mv);
+  }
+  // :362-393
+  template <typename GRAPH_T, typename MESSAGE_T = grape::EmptyType, typename FUNC_T>
+  void ParallelProcess(const GRAPH_T& frag, FUNC_T func) {
+    if (fnum_ == 1) return;   // nothing is ever received
+    gl_mm_view mv;
+    CHECK_GL(gl_mm_view_get(mm_, &mv));
+    dev::ProcessMsg<GRAPH_T, MESSAGE_T, FUNC_T><<<256, 256, 0, stream_.cuda_stream()>>>(mv, frag, func);
+    CHECK_CUDA(cudaGetLastError());
+    stream_.Sync();
+  }
+  template <typename MESSAGE_T = grape::EmptyType, typename FUNC_T>
+  void ParallelProcess(FUNC_T func) {
+    if (fnum_ == 1) return;
+    gl_mm_view mv;
+    CHECK_GL(gl_mm_view_get(mm_, &mv));
+    dev::ProcessRawMsg<MESSAGE_T, FUNC_T><<<256, 256, 0, stream_.cuda_stream()>>>(mv, func);
+    CHECK_CUDA(cudaGetLastError());
+    stream_.Sync();
+  }
 
  private:
+  static int HostAllReduce(void* user, void* inout, int n, int is_double, int op) {
+    auto* self = static_cast<GPUMessageManager*>(user);
+    const MPI_Op mop = op == 0 ? MPI_SUM : (op == 1 ? MPI_MIN : MPI_MAX);
+    return MPI_Allreduce(MPI_IN_PLACE, inout, n, is_double ? MPI_DOUBLE : MPI_INT64_T, mop, self->comm_spec_.comm());
+  }
+  void EnsureManager() {
+    // an app that never called InitBuffer still gets a working round protocol
+    if (!mm_) InitBuffer(4096, 4096);
+  }
+  void Release(bool collective) {
+    if (mm_) {
+      stream_.Sync();
+      gl_mm_destroy(mm_);
+      mm_ = nullptr;
+    }
+    if (comm_) {
+      // unmap the peers' landing areas, agree that everybody did, then free mine
+      gl_comm_close_peers(comm_);
+      if (collective && fnum_ > 1) MPI_Barrier(comm_spec_.comm());
+      gl_comm_destroy(comm_);
+      comm_ = nullptr;
+    }
+    capacity_ = 0;
+    if (fnum_ == 1 && collective) CHECK_GL(gl_mm_create(&mm_, nullptr));
+  }
+
+  grape::CommSpec comm_spec_;
+  fid_t fid_ = 0, fnum_ = 1;
+  gl_comm_t* comm_ = nullptr;
+  gl_mm_t* mm_ = nullptr;
+  unsigned long long capacity_ = 0;
   Stream stream_;
-  bool force_continue_ = false;
   bool terminate_ = false;
+  bool round_started_ = false;
 };
 
 // -------------------------------------------------------------- communicator --
-// grape/cuda/communication/communicator.h:41-95
+// grape/cuda/communication/communicator.h:41-95: one scalar per rank.  The
+// reference reduces host scalars with MPI and device scalars with NCCL; here
+// both go through MPI on the host (one word per superstep at most).
 class Communicator {
  public:
   Communicator() = default;
   virtual ~Communicator() = default;
-  void InitCommunicator(MPI_Comm, void*) {}
+  void InitCommunicator(MPI_Comm comm, void*) { comm_ = comm; }
   template <typename T>
-  void Sum(T msg_in, T& msg_out) { msg_out = msg_in; }
+  void Sum(T msg_in, T& msg_out) { reduce(msg_in, msg_out, MPI_SUM); }
   template <typename T>
-  void Min(T msg_in, T& msg_out) { msg_out = msg_in; }
+  void Min(T msg_in, T& msg_out) { reduce(msg_in, msg_out, MPI_MIN); }
   template <typename T>
-  void Max(T msg_in, T& msg_out) { msg_out = msg_in; }
+  void Max(T msg_in, T& msg_out) { reduce(msg_in, msg_out, MPI_MAX); }
   template <typename T>
-  std::vector<T> AllGather(T msg_in) { return std::vector<T>(1, msg_in); }
+  void Sum(T msg_in, T& msg_out, const Stream& stream) { stream.Sync(); reduce(msg_in, msg_out, MPI_SUM); }
+  template <typename T>
+  void Min(T msg_in, T& msg_out, const Stream& stream) { stream.Sync(); reduce(msg_in, msg_out, MPI_MIN); }
+  template <typename T>
+  void Max(T msg_in, T& msg_out, const Stream& stream) { stream.Sync(); reduce(msg_in, msg_out, MPI_MAX); }
+  template <typename T>
+  std::vector<T> AllGather(T msg_in) {
+    int n = 1;
+    MPI_Comm_size(comm_, &n);
+    std::vector<T> out((size_t) n);
+    MPI_Allgather(&msg_in, (int) sizeof(T), MPI_CHAR, out.data(), (int) sizeof(T), MPI_CHAR, comm_);
+    return out;
+  }
+
+ private:
+  template <typename T>
+  static MPI_Datatype mpi_type() {
+    static_assert(std::is_arithmetic<T>::value && !std::is_same<T, bool>::value, "unsupported type");
+    if (std::is_floating_point<T>::value) return sizeof(T) == 8 ? MPI_DOUBLE : MPI_FLOAT;
+    if (std::is_signed<T>::value) return sizeof(T) == 8 ? MPI_INT64_T : (sizeof(T) == 4 ? MPI_INT : MPI_INT8_T);
+    return sizeof(T) == 8 ? MPI_UINT64_T : (sizeof(T) == 4 ? MPI_UINT32_T : MPI_UINT8_T);
+  }
+  template <typename T>
+  void reduce(T in, T& out, MPI_Op op) {
+    out = in;
+    MPI_Allreduce(MPI_IN_PLACE, &out, 1, mpi_type<T>(), op, comm_);
+  }
+  MPI_Comm comm_ = MPI_COMM_WORLD;
 };
 template <typename APP_T>
 typename std::enable_if<std::is_base_of<Communicator, APP_T>::value>::type InitCommunicator(

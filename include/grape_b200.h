@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GL_ABI_VERSION 1
+#define GL_ABI_VERSION 2
 
 typedef enum {
   GL_OK = 0,
@@ -233,12 +233,90 @@ int gl_comm_create(gl_comm_t** out, const gl_comm_desc* d);
 int gl_comm_export(gl_comm_t*, void* handles_out, size_t bytes);
 /* all_handles: fnum consecutive exports, ordered by fid */
 int gl_comm_open(gl_comm_t*, const void* all_handles, size_t bytes);
+/* Unmaps the peers' landing areas (keeps the local one).  Teardown order for a
+ * group: every rank closes its peers, the group meets in a barrier, then each
+ * rank destroys its communicator -- nobody frees memory a peer still maps. */
+int gl_comm_close_peers(gl_comm_t*);
 void gl_comm_destroy(gl_comm_t*);
 /* Diagnostic: average time (us) of one kernel that stores `bytes` from local
  * memory into the next peer's (all_peers = 0) or every peer's (1) mirror slot
  * with 16-byte (vec16 = 1) or 4-byte stores, followed by a fence.sys per CTA.
  * Sizes the multi-GPU design decisions in DESIGN.md section 5. */
 int gl_comm_peer_write_us(gl_comm_t*, size_t bytes, int vec16, int all_peers, int reps, double* us_out);
+
+/* ------------------------------------------------------------------ *
+ * Message manager (Face 2): the halo exchange that the shimmed
+ * grape::cuda::GPUMessageManager / dev::MessageManager sit on
+ * (grape/cuda/parallel/gpu_message_manager.h:45-458,
+ *  grape/cuda/serialization/in_archive.h:36-169, out_archive.h:32-178,
+ *  grape/cuda/parallel/message_kernels.h:28-127).
+ * A producer kernel appends bytes for fragment d at
+ *   send_slot[d] + atomicAdd(&send_bytes[d], sizeof(item))
+ * -- send_slot[d] is fragment d's landing slot for this rank, mapped over
+ * NVLink / CUDA IPC: the store IS the transfer (no staging archive, no NCCL
+ * send/recv, no host size exchange).  gl_mm_finish_round publishes the byte
+ * counts, runs the device-side barrier + termination vote and flips the
+ * double buffer; what was sent in round r is readable through recv_slot /
+ * recv_bytes during round r+1 only (the reference's rule: messages are
+ * visible in the next IncEval).  Termination = no fragment sent a byte and
+ * none called force_continue (gpu_message_manager.h:413-430).
+ * ------------------------------------------------------------------ */
+typedef struct gl_mm gl_mm_t;
+typedef struct {
+  uint32_t fid, fnum;
+  int fid_offset;            /* gid = fid << fid_offset | lid (IdParser)        */
+  uint32_t id_mask;
+  uint32_t capacity_bytes;   /* per landing slot                               */
+  char* const* send_slot;    /* device table [fnum]: my slot at fragment d     */
+  uint32_t* send_bytes;      /* device [fnum]: bytes appended this round       */
+  const char* const* recv_slot;   /* device table [fnum]: what fragment s sent me last round */
+  const uint32_t* recv_bytes;     /* device [fnum]                              */
+} gl_mm_view;
+/* GPUMessageManager::Init (:160-194) on an OPENED communicator; fnum == 1: comm may be NULL */
+int gl_mm_create(gl_mm_t** out, gl_comm_t* comm);
+/* InitBuffer (:196-204): checks the per-peer capacities against the communicator's landing slots */
+int gl_mm_init_buffer(gl_mm_t*, size_t send_bytes_per_peer, size_t recv_bytes_per_peer);
+int gl_mm_start(gl_mm_t*);                         /* Start (:219) + round counter reset */
+int gl_mm_start_round(gl_mm_t*, void* stream);     /* StartARound (:225-231)             */
+int gl_mm_finish_round(gl_mm_t*, void* stream);    /* FinishARound (:237-303) + syncLengths (:400-431); synchronises the stream */
+int gl_mm_to_terminate(gl_mm_t*, int* out);        /* ToTerminate (:321)                 */
+int gl_mm_force_continue(gl_mm_t*);                /* ForceContinue (:338)               */
+int gl_mm_view_get(gl_mm_t*, gl_mm_view* out);     /* DeviceObject (:342-344): valid for the current round */
+uint64_t gl_mm_bytes_sent(gl_mm_t*);               /* GetMsgSize, accumulated over the query */
+void gl_mm_destroy(gl_mm_t*);
+
+/* Fixed-function consumers of ParallelProcess (:362-393): the received bytes
+ * are (uint32 gid, value) pairs -- thrust::pair<vid_t, MESSAGE_T> -- or bare
+ * uint32 gids (GL_MSG_SET_BIT); lid = gid & id_mask. */
+typedef enum {
+  GL_MSG_SET_BIT = 0,   /* bare gid: out_bitmap |= bit(lid)                     */
+  GL_MSG_MIN_U32 = 1,   /* if (v < atomicMin(state[lid], v)) out_bitmap |= bit   */
+  GL_MSG_MIN_F32 = 2,
+  GL_MSG_MIN_F64 = 3,
+  GL_MSG_ADD_F32 = 4,   /* atomicAdd(state[lid], v)                              */
+  GL_MSG_ADD_F64 = 5
+} gl_msg_op_kind;
+typedef struct {
+  int kind;               /* gl_msg_op_kind                                     */
+  void* state;            /* device array indexed by lid                        */
+  uint32_t* out_bitmap;   /* may be NULL                                        */
+} gl_msg_op;
+int gl_mm_process(gl_mm_t*, void* stream, const gl_msg_op* op, uint64_t* items_host /* may be NULL */);
+
+/* Fixed-function producer: the "ForEach over outer vertices +
+ * SyncStateOnOuterVertex[WarpOpt]" idiom (e.g. cuda/sssp/sssp.h:295-304).  For
+ * every set bit v of `remote` inside the fragment's outer range, appends
+ * (gid(v)[, state[v]]) to the owner's landing slot (value_bytes: 0 = bare gid,
+ * 4 or 8 = thrust::pair<vid_t, value> layout) and clears the bit when
+ * clear_bits != 0. */
+int gl_mm_send_outer(gl_mm_t*, void* stream, const gl_frag_t* frag, uint32_t* remote_bitmap,
+                     const void* state, int value_bytes, int clear_bits);
+
+/* cuda::Communicator::Sum/Min/Max on one host scalar
+ * (grape/cuda/communication/communicator.h:41-84,160-172): device-side peer
+ * all-reduce, bit-identical on every rank (fixed fid order).
+ * dtype: 0 int64, 1 double; op: 0 sum, 1 min, 2 max.  Synchronises `stream`. */
+int gl_allreduce(gl_mm_t*, void* stream, void* inout_host, int dtype, int op);
 
 /* ------------------------------------------------------------------ *
  * PIE apps (PEval / IncEval / Output): replaces GPUWorker::{Init,Query}
@@ -340,6 +418,15 @@ int gl_edge_scan_queue(const gl_frag_t*, void* stream, const uint32_t* queue,
  * Replaces the O(V) ForEach + AppendWarp idiom (cuda/sssp/sssp.h:223-232). */
 int gl_compact_bitmap(void* stream, const uint32_t* bitmap, uint32_t n_bits,
                       uint32_t* queue_out, uint32_t* count_host);
+
+/* Frontier containers (grape/cuda/utils/bitset.h:32-196, vertex_set.h:30-163):
+ * a DenseVertexSet is a device bitmap of ceil(nbits/32) words; VertexArray is
+ * a plain device array (gl_dev_alloc + gl_dev_h2d / gl_dev_d2h); Queue = the
+ * (queue_out, count) pair gl_compact_bitmap fills. */
+int gl_bitmap_create(uint32_t** out, uint64_t nbits);               /* zeroed */
+int gl_bitmap_clear(void* stream, uint32_t* bitmap, uint64_t nbits);  /* Clear(stream) */
+int gl_bitmap_count(void* stream, const uint32_t* bitmap, uint64_t nbits, uint64_t* count_host); /* Count(stream): syncs */
+int gl_bitmap_destroy(uint32_t* bitmap);
 
 /* device scratch helpers so a C/ctypes caller can run the primitives */
 int gl_dev_alloc(void** out, size_t bytes);

@@ -83,7 +83,10 @@ SYMBOLS = [
     "gl_frag_build_rmat", "gl_rmat_edges_host", "gl_frag_get_info", "gl_frag_view_get", "gl_frag_copy_csr",
     "gl_frag_copy_ovgid", "gl_frag_oid2lid", "gl_frag_max_degree_vertex", "gl_frag_offload",
     "gl_frag_reload", "gl_frag_destroy", "gl_comm_create", "gl_comm_export", "gl_comm_open",
-    "gl_comm_destroy", "gl_comm_peer_write_us", "gl_app_config_default", "gl_app_create", "gl_app_query", "gl_app_result",
+    "gl_comm_destroy", "gl_comm_close_peers", "gl_comm_peer_write_us", "gl_mm_create", "gl_mm_init_buffer", "gl_mm_start",
+    "gl_mm_start_round", "gl_mm_finish_round", "gl_mm_to_terminate", "gl_mm_force_continue", "gl_mm_view_get",
+    "gl_mm_bytes_sent", "gl_mm_destroy", "gl_mm_process", "gl_mm_send_outer", "gl_allreduce", "gl_bitmap_create",
+    "gl_bitmap_clear", "gl_bitmap_count", "gl_bitmap_destroy", "gl_app_config_default", "gl_app_create", "gl_app_query", "gl_app_result",
     "gl_app_result_oids", "gl_app_destroy", "gl_edge_scan_queue", "gl_compact_bitmap", "gl_dev_alloc",
     "gl_dev_free", "gl_dev_memset", "gl_dev_h2d", "gl_dev_d2h", "gl_dev_sync", "gl_kernel_launch_count",
     "gl_host_alloc_pinned", "gl_host_free_pinned",
@@ -104,6 +107,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.gl_last_error.restype = C.c_char_p
         L.gl_kernel_launch_count.restype = C.c_uint64
+        L.gl_mm_bytes_sent.restype = C.c_uint64
+        L.gl_mm_destroy.restype = None
         for f in ("gl_frag_destroy", "gl_comm_destroy", "gl_app_destroy", "gl_app_config_default"):
             getattr(L, f).restype = None
         _LIB = L
@@ -304,6 +309,83 @@ class Comm:
         if self.h:
             lib().gl_comm_destroy(self.h)
             self.h = None
+
+
+class MsgOp(C.Structure):
+    _fields_ = [("kind", C.c_int), ("state", C.c_void_p), ("out_bitmap", C.c_void_p)]
+
+
+class MmView(C.Structure):
+    _fields_ = [("fid", C.c_uint32), ("fnum", C.c_uint32), ("fid_offset", C.c_int), ("id_mask", C.c_uint32),
+                ("capacity_bytes", C.c_uint32), ("send_slot", C.c_void_p), ("send_bytes", C.c_void_p),
+                ("recv_slot", C.c_void_p), ("recv_bytes", C.c_void_p)]
+
+
+MSG_OPS = {"set_bit": 0, "min_u32": 1, "min_f32": 2, "min_f64": 3, "add_f32": 4, "add_f64": 5}
+
+
+class MessageManager:
+    """Face 2 of the boundary (gl_mm_*): GPUMessageManager's round protocol and
+    the fixed-function producer / consumer kernels, on the legacy stream."""
+
+    def __init__(self, comm=None):
+        self.h = C.c_void_p()
+        check(lib().gl_mm_create(C.byref(self.h), comm.h if comm else None))
+
+    def init_buffer(self, send_bytes, recv_bytes):
+        check(lib().gl_mm_init_buffer(self.h, C.c_size_t(send_bytes), C.c_size_t(recv_bytes)))
+
+    def start(self):
+        check(lib().gl_mm_start(self.h))
+
+    def start_round(self):
+        check(lib().gl_mm_start_round(self.h, None))
+
+    def finish_round(self):
+        check(lib().gl_mm_finish_round(self.h, None))
+
+    def to_terminate(self):
+        t = C.c_int()
+        check(lib().gl_mm_to_terminate(self.h, C.byref(t)))
+        return bool(t.value)
+
+    def force_continue(self):
+        check(lib().gl_mm_force_continue(self.h))
+
+    def view(self):
+        v = MmView()
+        check(lib().gl_mm_view_get(self.h, C.byref(v)))
+        return v
+
+    def bytes_sent(self):
+        return int(lib().gl_mm_bytes_sent(self.h))
+
+    def process(self, kind, state=None, out_bitmap=None):
+        op = MsgOp(MSG_OPS[kind], state.ptr if state is not None else None,
+                   out_bitmap.ptr if out_bitmap is not None else None)
+        n = C.c_uint64()
+        check(lib().gl_mm_process(self.h, None, C.byref(op), C.byref(n)))
+        return n.value
+
+    def send_outer(self, frag, remote_bitmap, state=None, value_bytes=0, clear_bits=True):
+        check(lib().gl_mm_send_outer(self.h, None, frag.h, remote_bitmap.ptr,
+                                     state.ptr if state is not None else None, int(value_bytes), int(clear_bits)))
+
+    def allreduce(self, value, is_double=False, op=0):
+        v = C.c_double(value) if is_double else C.c_int64(int(value))
+        check(lib().gl_allreduce(self.h, None, C.byref(v), 1 if is_double else 0, int(op)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            lib().gl_mm_destroy(self.h)
+            self.h = None
+
+
+def bitmap_count(bitmap_dev, nbits):
+    n = C.c_uint64()
+    check(lib().gl_bitmap_count(None, C.cast(bitmap_dev.ptr, C.POINTER(C.c_uint32)), C.c_uint64(nbits), C.byref(n)))
+    return n.value
 
 
 class App:

@@ -701,6 +701,17 @@ int gl_comm_open(gl_comm_t* c, const void* all, size_t bytes) {
   return GL_OK;
 }
 
+int gl_comm_close_peers(gl_comm_t* c) {
+  GL_ARG(c, "null argument");
+  for (uint32_t p = 0; p < c->fnum; ++p)
+    if (p != c->fid && c->peer_base[p]) {
+      cudaIpcCloseMemHandle(c->peer_base[p]);
+      c->peer_base[p] = nullptr;
+    }
+  c->opened = c->fnum == 1;
+  return GL_OK;
+}
+
 void gl_comm_destroy(gl_comm_t* c) {
   if (!c) return;
   for (uint32_t p = 0; p < c->fnum; ++p)
@@ -770,3 +781,328 @@ extern "C" int gl_comm_peer_write_us(gl_comm_t* c, size_t bytes, int vec16, int 
   cudaFree(src);
   return GL_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Face 2 of the boundary: gl_mm_* / gl_allreduce (include/grape_b200.h).
+// A gl_mm is the library's MessageManager with byte-granular slots
+// (item_bytes = 1): the shimmed grape::cuda::GPUMessageManager of
+// compat/grape/cuda/b200_compat.h runs the reference's unchanged apps on it.
+// ---------------------------------------------------------------------------
+struct gl_mm {
+  gl::MessageManager mm;
+  gl_comm* comm = nullptr;
+  bool owns_single = false;   // fnum == 1 and no communicator was given
+  gl::ScanCtrl* d_ctrl = nullptr;
+};
+
+namespace gl {
+namespace {
+template <typename V>
+struct GidVal {
+  uint32_t gid;
+  V val;
+};
+template <>
+struct GidVal<double> {
+  uint32_t gid, pad;
+  double val;
+};
+// one launch over all sources; items are thrust::pair<vid_t, V>-shaped
+template <typename V, int KIND>
+__global__ void __launch_bounds__(256) k_mm_process(gl_mm_view mv, V* state, uint32_t* out_bitmap,
+                                                     unsigned long long* n_items) {
+  unsigned long long mine = 0;
+  for (uint32_t src = 0; src < mv.fnum; ++src) {
+    if (src == mv.fid) continue;
+    uint32_t bytes = mv.recv_bytes[src];
+    if (bytes > mv.capacity_bytes) bytes = mv.capacity_bytes;
+    if (KIND == GL_MSG_SET_BIT) {
+      const uint32_t n = bytes / 4;
+      const uint32_t* g = (const uint32_t*) mv.recv_slot[src];
+      for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t lid = __ldcg(g + i) & mv.id_mask;
+        if (out_bitmap) atomicOr(out_bitmap + (lid >> 5), 1u << (lid & 31));
+        ++mine;
+      }
+    } else {
+      using It = GidVal<V>;
+      const uint32_t n = bytes / (uint32_t) sizeof(It);
+      const It* items = (const It*) mv.recv_slot[src];
+      for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t lid = __ldcg(&items[i].gid) & mv.id_mask;
+        const V v = __ldcg(&items[i].val);
+        bool improved = false;
+        if (KIND == GL_MSG_MIN_U32) improved = v < atomicMin((unsigned int*) (state + lid), (unsigned int) v);
+        else if (KIND == GL_MSG_MIN_F32) improved = v < atomic_min_f32_nonneg((float*) (state + lid), (float) v);
+        else if (KIND == GL_MSG_MIN_F64) improved = v < atomic_min_f64_nonneg((double*) (state + lid), (double) v);
+        else atomicAdd(state + lid, v);
+        if (improved && out_bitmap) atomicOr(out_bitmap + (lid >> 5), 1u << (lid & 31));
+        ++mine;
+      }
+    }
+  }
+  mine = warp_sum(mine);
+  if (lane_id() == 0 && mine && n_items) atomicAdd(n_items, mine);
+}
+}  // namespace
+}  // namespace gl
+
+namespace gl {
+namespace {
+template <int VB>
+struct OuterItem;
+template <>
+struct OuterItem<0> { uint32_t gid; };
+template <>
+struct OuterItem<4> { uint32_t gid; uint32_t val; };
+template <>
+struct OuterItem<8> { uint32_t gid, pad; unsigned long long val; };
+
+// one thread per outer copy; lanes of a warp bound for the same owner share a
+// single byte reservation in that owner's landing slot
+template <int VB>
+__global__ void __launch_bounds__(256) k_mm_send_outer(gl_mm_view mv, uint32_t* remote, uint32_t ivnum, uint32_t ovnum,
+                                                        const uint32_t* __restrict__ ovgid, const void* state,
+                                                        int clear_bits) {
+  using It = OuterItem<VB>;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (ovnum + stride - 1) / stride;
+  uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t r = 0; r < rounds; ++r, o += stride) {
+    bool pred = false;
+    uint32_t dst = 0;
+    It it;
+    memset(&it, 0, sizeof(it));
+    if (o < ovnum) {
+      const uint32_t v = ivnum + o;
+      if (bit_test(remote, v)) {
+        pred = true;
+        it.gid = ovgid[o];
+        dst = it.gid >> mv.fid_offset;
+        if constexpr (VB == 4) it.val = ((const uint32_t*) state)[v];
+        if constexpr (VB == 8) it.val = ((const unsigned long long*) state)[v];
+      }
+    }
+    const uint32_t active = __ballot_sync(0xffffffffu, pred);
+    if (pred) {
+      const uint32_t peers = __match_any_sync(active, dst);
+      const uint32_t leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (lane_id() == leader) base = atomicAdd(mv.send_bytes + dst, (uint32_t) (__popc(peers) * sizeof(It)));
+      base = __shfl_sync(peers, base, leader);
+      const uint32_t off = base + __popc(peers & ((1u << lane_id()) - 1)) * (uint32_t) sizeof(It);
+      if (off + sizeof(It) <= mv.capacity_bytes) *(It*) (mv.send_slot[dst] + off) = it;
+    }
+  }
+  (void) clear_bits;
+}
+__global__ void k_clear_bit_range(uint32_t* bm, uint32_t lo, uint32_t hi) {
+  const uint32_t w_lo = lo >> 5, w_hi = (hi + 31) >> 5;
+  for (uint32_t w = w_lo + blockIdx.x * blockDim.x + threadIdx.x; w < w_hi; w += gridDim.x * blockDim.x) {
+    uint32_t keep = 0;
+    const uint32_t b0 = w << 5;
+    if (b0 < lo) keep |= (1u << (lo - b0)) - 1u;
+    if (b0 + 32 > hi) keep |= hi > b0 ? ~((1u << (hi - b0)) - 1u) : 0xFFFFFFFFu;
+    bm[w] &= keep;
+  }
+}
+__global__ void k_bitmap_count(const uint32_t* bm, uint64_t nbits, unsigned long long* out) {
+  const uint64_t words = (nbits + 31) / 32;
+  unsigned long long c = 0;
+  for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t) gridDim.x * blockDim.x) {
+    uint32_t w = bm[i];
+    if (i == words - 1 && (nbits & 31)) w &= (1u << (nbits & 31)) - 1u;
+    c += __popc(w);
+  }
+  c = warp_sum(c);
+  if (lane_id() == 0 && c) atomicAdd(out, c);
+}
+}  // namespace
+}  // namespace gl
+
+extern "C" {
+
+int gl_bitmap_create(uint32_t** out, uint64_t nbits) {
+  GL_ARG(out, "null argument");
+  DeviceInfo* di;
+  GL_TRY(device_info(&di));
+  const size_t bytes = sizeof(uint32_t) * ((size_t) ((nbits + 31) / 32) + 1);
+  GL_CUDA(cudaMalloc(out, bytes));
+  GL_CUDA(cudaMemset(*out, 0, bytes));
+  return GL_OK;
+}
+int gl_bitmap_clear(void* stream, uint32_t* bitmap, uint64_t nbits) {
+  GL_ARG(bitmap, "null argument");
+  GL_CUDA(cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * (size_t) ((nbits + 31) / 32), (cudaStream_t) stream));
+  return GL_OK;
+}
+int gl_bitmap_count(void* stream, const uint32_t* bitmap, uint64_t nbits, uint64_t* count_host) {
+  GL_ARG(bitmap && count_host, "null argument");
+  cudaStream_t s = (cudaStream_t) stream;
+  unsigned long long* d = nullptr;
+  GL_CUDA(cudaMalloc(&d, 8));
+  GL_CUDA(cudaMemsetAsync(d, 0, 8, s));
+  if (nbits) GL_LAUNCH(k_bitmap_count, 148 * 4, 256, s, bitmap, nbits, d);
+  unsigned long long h = 0;
+  GL_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, s));
+  GL_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d);
+  *count_host = h;
+  return GL_OK;
+}
+int gl_bitmap_destroy(uint32_t* bitmap) {
+  if (bitmap) GL_CUDA(cudaFree(bitmap));
+  return GL_OK;
+}
+
+int gl_mm_send_outer(gl_mm_t* m, void* stream, const gl_frag_t* frag, uint32_t* remote, const void* state,
+                     int value_bytes, int clear_bits) {
+  GL_ARG(m && frag && remote, "null argument");
+  GL_ARG(value_bytes == 0 || ((value_bytes == 4 || value_bytes == 8) && state), "gl_mm_send_outer: value_bytes must be 0, 4 or 8");
+  if (m->mm.fnum == 1 || frag->ovnum == 0) return GL_OK;
+  cudaStream_t s = (cudaStream_t) stream;
+  gl_mm_view mv;
+  GL_TRY(gl_mm_view_get(m, &mv));
+  const int grid = 148 * 4;
+  if (value_bytes == 0) GL_LAUNCH(k_mm_send_outer<0>, grid, 256, s, mv, remote, frag->ivnum, frag->ovnum, frag->ovgid, state, 0);
+  else if (value_bytes == 4) GL_LAUNCH(k_mm_send_outer<4>, grid, 256, s, mv, remote, frag->ivnum, frag->ovnum, frag->ovgid, state, 0);
+  else GL_LAUNCH(k_mm_send_outer<8>, grid, 256, s, mv, remote, frag->ivnum, frag->ovnum, frag->ovgid, state, 0);
+  if (clear_bits) GL_LAUNCH(k_clear_bit_range, 148, 256, s, remote, frag->ivnum, frag->ivnum + frag->ovnum);
+  return GL_OK;
+}
+
+int gl_mm_create(gl_mm_t** out, gl_comm_t* comm) {
+  GL_ARG(out, "null argument");
+  DeviceInfo* di;
+  GL_TRY(device_info(&di));
+  if (comm && !comm->opened) {
+    set_error("gl_mm_create: the communicator is not opened (gl_comm_open)");
+    return GL_ERR_STATE;
+  }
+  gl_mm* m = new gl_mm;
+  m->comm = comm;
+  gl_frag_view fv;
+  memset(&fv, 0, sizeof(fv));
+  fv.fid = comm ? comm->fid : 0;
+  fv.fnum = comm ? comm->fnum : 1;
+  id_parser_init(fv.fnum, &fv.fid_offset, &fv.id_mask);
+  int st = m->mm.Init(comm, fv, 1);
+  if (st != GL_OK) {
+    delete m;
+    return st;
+  }
+  if (cudaMalloc(&m->d_ctrl, sizeof(ScanCtrl)) != cudaSuccess) {
+    m->mm.Destroy();
+    delete m;
+    set_error("gl_mm_create: device allocation failed");
+    return GL_ERR_NOMEM;
+  }
+  *out = m;
+  return GL_OK;
+}
+
+int gl_mm_init_buffer(gl_mm_t* m, size_t send_bytes, size_t recv_bytes) {
+  GL_ARG(m, "null argument");
+  if (m->mm.fnum == 1) return GL_OK;
+  const size_t need = send_bytes > recv_bytes ? send_bytes : recv_bytes;
+  if (need > m->comm->landing_bytes) {
+    set_error("gl_mm_init_buffer: %zu bytes per peer exceed the communicator's landing slot (%zu)", need,
+              m->comm->landing_bytes);
+    return GL_ERR_ARG;
+  }
+  return GL_OK;
+}
+
+int gl_mm_start(gl_mm_t* m) {
+  GL_ARG(m, "null argument");
+  m->mm.Start();
+  return GL_OK;
+}
+int gl_mm_start_round(gl_mm_t* m, void* stream) {
+  GL_ARG(m, "null argument");
+  return m->mm.StartARound((cudaStream_t) stream);
+}
+int gl_mm_finish_round(gl_mm_t* m, void* stream) {
+  GL_ARG(m, "null argument");
+  return m->mm.FinishARound((cudaStream_t) stream);
+}
+int gl_mm_to_terminate(gl_mm_t* m, int* out) {
+  GL_ARG(m && out, "null argument");
+  *out = m->mm.ToTerminate() ? 1 : 0;
+  return GL_OK;
+}
+int gl_mm_force_continue(gl_mm_t* m) {
+  GL_ARG(m, "null argument");
+  m->mm.ForceContinue();
+  return GL_OK;
+}
+int gl_mm_view_get(gl_mm_t* m, gl_mm_view* out) {
+  GL_ARG(m && out, "null argument");
+  const MsgView v = m->mm.view();
+  memset(out, 0, sizeof(*out));
+  out->fid = v.fid;
+  out->fnum = v.fnum;
+  out->fid_offset = v.fid_offset;
+  out->id_mask = v.id_mask;
+  out->capacity_bytes = v.capacity;
+  out->send_slot = v.send_slot;
+  out->send_bytes = v.send_count;
+  out->recv_slot = v.recv_slot;
+  out->recv_bytes = v.recv_count;
+  return GL_OK;
+}
+uint64_t gl_mm_bytes_sent(gl_mm_t* m) { return m ? m->mm.bytes_sent : 0; }
+void gl_mm_destroy(gl_mm_t* m) {
+  if (!m) return;
+  m->mm.Destroy();
+  if (m->d_ctrl) cudaFree(m->d_ctrl);
+  delete m;
+}
+
+int gl_mm_process(gl_mm_t* m, void* stream, const gl_msg_op* op, uint64_t* items_host) {
+  GL_ARG(m && op, "null argument");
+  GL_ARG(op->kind == GL_MSG_SET_BIT || op->state, "gl_mm_process: state array required");
+  if (items_host) *items_host = 0;
+  if (m->mm.fnum == 1) return GL_OK;
+  cudaStream_t s = (cudaStream_t) stream;
+  gl_mm_view mv;
+  GL_TRY(gl_mm_view_get(m, &mv));
+  unsigned long long* cnt = (unsigned long long*) m->d_ctrl;
+  GL_CUDA(cudaMemsetAsync(cnt, 0, 8, s));
+  const int grid = 148 * 4;
+  switch (op->kind) {
+    case GL_MSG_SET_BIT: GL_LAUNCH((k_mm_process<uint32_t, GL_MSG_SET_BIT>), grid, 256, s, mv, (uint32_t*) nullptr, op->out_bitmap, cnt); break;
+    case GL_MSG_MIN_U32: GL_LAUNCH((k_mm_process<uint32_t, GL_MSG_MIN_U32>), grid, 256, s, mv, (uint32_t*) op->state, op->out_bitmap, cnt); break;
+    case GL_MSG_MIN_F32: GL_LAUNCH((k_mm_process<float, GL_MSG_MIN_F32>), grid, 256, s, mv, (float*) op->state, op->out_bitmap, cnt); break;
+    case GL_MSG_MIN_F64: GL_LAUNCH((k_mm_process<double, GL_MSG_MIN_F64>), grid, 256, s, mv, (double*) op->state, op->out_bitmap, cnt); break;
+    case GL_MSG_ADD_F32: GL_LAUNCH((k_mm_process<float, GL_MSG_ADD_F32>), grid, 256, s, mv, (float*) op->state, op->out_bitmap, cnt); break;
+    case GL_MSG_ADD_F64: GL_LAUNCH((k_mm_process<double, GL_MSG_ADD_F64>), grid, 256, s, mv, (double*) op->state, op->out_bitmap, cnt); break;
+    default:
+      set_error("gl_mm_process: unknown op kind %d", op->kind);
+      return GL_ERR_ARG;
+  }
+  if (items_host) {
+    unsigned long long h = 0;
+    GL_CUDA(cudaMemcpyAsync(&h, cnt, 8, cudaMemcpyDeviceToHost, s));
+    GL_CUDA(cudaStreamSynchronize(s));
+    *items_host = h;
+  }
+  return GL_OK;
+}
+
+int gl_allreduce(gl_mm_t* m, void* stream, void* inout_host, int dtype, int op) {
+  GL_ARG(m && inout_host, "null argument");
+  GL_ARG(op >= 0 && op <= 2 && (dtype == 0 || dtype == 1), "gl_allreduce: bad dtype/op");
+  if (m->mm.fnum == 1) return GL_OK;
+  // the unused lanes carry the operation's identity
+  long long a = 0, b = 0;
+  double c = 0;
+  if (op == 1) { a = b = INT64_MAX; c = 1.7976931348623157e308; }
+  if (op == 2) { a = b = INT64_MIN; c = -1.7976931348623157e308; }
+  if (dtype == 0) a = *(long long*) inout_host; else c = *(double*) inout_host;
+  GL_TRY(m->mm.PeerAllReduce((cudaStream_t) stream, &a, &b, &c, op));
+  if (dtype == 0) *(long long*) inout_host = a; else *(double*) inout_host = c;
+  return GL_OK;
+}
+
+}  // extern "C"

@@ -312,8 +312,11 @@ GL_DEV void frontier_scan_phase(ScanSmem<typename Op::Meta>& sm,
   uint32_t st;
   if (threadIdx.x == 0) sm.hubn = 0;
   __syncthreads();
+  // bits at positions >= nverts (outer copies sharing the last word when nverts
+  // is not a multiple of 32) are not frontier vertices of this scan
+  const uint32_t last_w = nverts >> 5, last_mask = (1u << (nverts & 31)) - 1u;
   while (next_super_tile(sm, &ctrl->tile_ticket, nverts,
-                         [&](uint32_t w) { return frontier[w]; }, &st)) {
+                         [&](uint32_t w) { return w == last_w ? (frontier[w] & last_mask) : frontier[w]; }, &st)) {
     for (int k = 0; k < kSuperTiles; ++k) {
       if (!sm.nz[k]) continue;  // uniform
       // expand the sub-tile's set bits: thread t owns bits [4t, 4t+4)

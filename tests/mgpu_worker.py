@@ -40,7 +40,49 @@ def main():
         dist.all_gather_object(out, arr)
         return np.concatenate(out)
 
-    for wmode, apps in ((0, ["bfs", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "wcc_opt", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp"])):
+    def face2_sssp(frag, comm, source):
+        """SSSP written against Face 2 only (gl_mm_* + gl_edge_scan_queue +
+        gl_compact_bitmap): what a C host would do per IncEval (cuda/sssp/sssp.h:173-305)."""
+        capi = pkg.capi
+        tv = frag.ivnum + frag.ovnum
+        words = (tv + 31) // 32 + 1
+        dist_h = np.full(tv, np.finfo(np.float32).max, dtype=np.float32)
+        active_h = np.zeros(words, dtype=np.uint32)
+        lid = frag.oid2lid(source)
+        if lid is not None:
+            dist_h[lid] = 0.0
+            active_h[lid >> 5] |= np.uint32(1 << (lid & 31))
+        dist = capi.DeviceArray(dist_h)
+        active = capi.DeviceArray(active_h)
+        nxt = capi.DeviceArray(np.zeros(words, dtype=np.uint32))
+        queue = capi.DeviceArray(nbytes=4 * (frag.ivnum + 1))
+        mm = capi.MessageManager(comm)
+        mm.init_buffer(8 * frag.ovnum, 8 * frag.ivnum)
+        mm.start()
+        mm.start_round()
+        mm.force_continue()          # PEval
+        mm.finish_round()
+        rounds = 1
+        while not mm.to_terminate():
+            mm.start_round()
+            mm.process("min_f32", state=dist, out_bitmap=active)
+            n = capi.compact_bitmap(active, frag.ivnum, queue)
+            active.fill(0)
+            if n:
+                capi.edge_scan_queue(frag, queue, n, "min_relax_f32", "cm", state=dist, out_bitmap=nxt, use_weight=1)
+            mm.send_outer(frag, nxt, state=dist, value_bytes=4, clear_bits=True)
+            if capi.bitmap_count(nxt, frag.ivnum) > 0:
+                mm.force_continue()
+            active, nxt = nxt, active
+            mm.finish_round()
+            rounds += 1
+        out = dist.download(np.float32, tv)[: frag.ivnum].astype(np.float64)
+        out[out == np.finfo(np.float32).max] = np.finfo(np.float64).max
+        total = mm.allreduce(mm.bytes_sent())
+        mm.close()
+        return out, rounds, total
+
+    for wmode, apps in ((0, ["bfs", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "wcc_opt", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp", "face2_sssp"])):
         n = 1 << scale
         frag = pkg.Fragment.rmat(scale, 16, seed=17, weight_mode=wmode, fid=rank, fnum=world)
         comm = gdist.make_comm(rank, world, frag.ivnum)
@@ -73,6 +115,17 @@ def main():
                 cfg = dict(pr_delta=0.85, max_round=10, pr_pull=1 if name.endswith("pull") else 0)
             elif name == "cdlp":
                 cfg = dict(max_round=5)
+            if name == "face2_sssp":
+                res, rounds, total = face2_sssp(frag, comm, source)
+                got = gather(res)
+                if rank == 0:
+                    ok = np.array_equal(got, g.sssp(source)[0])
+                    print("[mgpu] %-13s fnum=%d scale=%d supersteps=%d msg_bytes=%d %s"
+                          % (name, world, scale, rounds, total, "OK" if ok else "MISMATCH"), flush=True)
+                    if not ok:
+                        failures.append(name)
+                dist.barrier()
+                continue
             app = pkg.App(kind, frag, comm, **cfg)
             st = app.query()
             got = gather(app.result())

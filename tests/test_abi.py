@@ -31,7 +31,7 @@ def test_python_mirror_lists_the_same_symbols():
 
 
 def test_abi_version():
-    assert pkg().lib().gl_abi_version() == 1
+    assert pkg().lib().gl_abi_version() == 2
 
 
 def test_struct_sizes_match_the_header():
