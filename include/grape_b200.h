@@ -351,7 +351,9 @@ typedef struct {
                             [1] 1: BFS without the hub-first shadow CSR
                             [2] BFS pull->push threshold divisor (default 24)
                             [3] >=4: number of BFS level bitmaps (forces spills)
-                            [5] 1: PageRank pull gathers f32 contributions      */
+                            [5] 1: PageRank pull gathers f32 contributions
+                            [6] 1: BFS result as an int64 device array + one D2H
+                                   (default: u8 depths over PCIe, widened on the host) */
 } gl_app_config;
 void gl_app_config_default(gl_app_config*);
 

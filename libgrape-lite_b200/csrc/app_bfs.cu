@@ -25,6 +25,8 @@
 //    keep one launch group per superstep around the halo exchange.
 #include <cooperative_groups.h>
 
+#include <thread>
+
 #include "apps_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -909,6 +911,24 @@ __global__ void k_depth_from_levels(const uint32_t* lv, uint32_t words,
   out[i] = d;
 }
 
+// depth as ONE byte per vertex (0xFF = unreached): 8x fewer bytes across PCIe
+// than the reference's int64 depth array; gl_app_result widens on the host
+__global__ void k_depth_u8_from_levels(const uint32_t* lv, uint32_t words, uint32_t nlevels, uint32_t n,
+                                       const uint32_t* perm, uint8_t* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t pi = perm ? perm[i] : i;
+  const uint32_t w = pi >> 5, m = 1u << (pi & 31);
+  uint32_t d = 0xFFu;
+  for (uint32_t l = 0; l < nlevels; ++l) {
+    if (lv[(size_t) l * words + w] & m) {
+      d = l;
+      break;
+    }
+  }
+  out[i] = (uint8_t) d;
+}
+
 struct BfsApp : gl_app {
   uint32_t *lv = nullptr, *vis = nullptr, *remote = nullptr, *hub_nbr = nullptr;
   int64_t* out64 = nullptr;
@@ -954,6 +974,10 @@ struct BfsApp : gl_app {
     cudaFree(col_p);
     cudaFree(rp_p);
     cudaFree(nz_in);
+    cudaFree(d_out8);
+    if (h_out8) cudaFreeHost(h_out8);
+    for (auto e : ev8)
+      if (e) cudaEventDestroy(e);
   }
   size_t ResultElemBytes() const override { return sizeof(int64_t); }
 
@@ -1336,9 +1360,42 @@ struct BfsApp : gl_app {
   bool step_pull = false;
   bool rounds_noted = false;   // PEval's vote carries no engine counters
 
+  // compact result path: u8 depths, chunked D2H into pinned staging, widened to
+  // the reference's int64 (bfs_context.h:31 depth_type) by host threads while the
+  // next chunk is still crossing PCIe
+  uint8_t *d_out8 = nullptr, *h_out8 = nullptr;
+  cudaEvent_t ev8[8] = {};
+  int ResultCompact(int64_t* host_out, uint32_t nl) {
+    cudaStream_t s = eng.stream;
+    const uint32_t n = fv.ivnum;
+    if (!d_out8) {
+      GL_CUDA(cudaMalloc(&d_out8, n));
+      GL_CUDA(cudaMallocHost(&h_out8, n));
+      for (auto& e : ev8) GL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    GL_LAUNCH(k_depth_u8_from_levels, (n + 255) / 256, 256, s, lv, (uint32_t) words, nl, n, perm, d_out8);
+    const uint32_t nchunks = n >= (1u << 20) ? 8 : 1;
+    const uint32_t per = ((n + nchunks - 1) / nchunks + 63) & ~63u;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+      const uint32_t b = std::min(n, c * per), e = std::min(n, b + per);
+      if (e > b) GL_CUDA(cudaMemcpyAsync(h_out8 + b, d_out8 + b, e - b, cudaMemcpyDeviceToHost, s));
+      GL_CUDA(cudaEventRecord(ev8[c], s));
+    }
+    static const int kThreads = std::max(1, std::min<int>(16, (int) std::thread::hardware_concurrency() / 2));
+    for (uint32_t c = 0; c < nchunks; ++c) {
+      const uint32_t b = std::min(n, c * per), e = std::min(n, b + per);
+      GL_CUDA(cudaEventSynchronize(ev8[c]));
+      const uint8_t* in = h_out8;
+#pragma omp parallel for num_threads(kThreads) schedule(static)
+      for (int64_t i = (int64_t) b; i < (int64_t) e; ++i) host_out[i] = in[i] == 0xFFu ? INT64_MAX : (int64_t) in[i];
+    }
+    return GL_OK;
+  }
+
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
     uint32_t nl = std::min<uint32_t>(max_lv, used_lv + 1);
+    if (!spilled && depth_base == 0 && nl <= 254 && cfg.reserved[6] == 0) return ResultCompact((int64_t*) host_out, nl);
     GL_LAUNCH(k_depth_from_levels, (fv.ivnum + 255) / 256, 256, eng.stream, lv, (uint32_t) words, nl, fv.ivnum, perm,
               depth_base, spilled ? spill : nullptr, out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(int64_t) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));

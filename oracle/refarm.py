@@ -33,11 +33,11 @@ def ref_binary():
     return p if os.path.exists(p) else None
 
 
-def run(app, scale, edgefactor=16, seed=1, reuse=False, repeat=1, keep=1):
+def run(app, scale, edgefactor=16, seed=1, reuse=False, repeat=1, keep=1, opt=False):
     exe = ref_binary()
     if exe is not None:
         from oracle import refdriver
-        return refdriver.run(exe, app, scale, edgefactor, seed, repeat=repeat, keep=keep)
+        return refdriver.run(exe, app, scale, edgefactor, seed, repeat=repeat, keep=keep, opt=opt)
     g, src, dst, w = _graph(scale, edgefactor, seed, app == "sssp")
     source = g.max_degree_vertex()
     rp, _, _ = g.csr()

@@ -67,42 +67,37 @@ def parse_output(text, dtype=float):
     return o[k], v[k]
 
 
-_graph_cache = {}
+def run_rmat(app, scale, edgefactor=16, seed=1, repeat=1, opt=False, threads=0, timeout=3600, out=None):
+    """Runs the reference CPU app on bench.py's synthetic input, generated INSIDE ref_driver
+    (oracle/rmat_gen.h) -- nothing of the product is loaded.  -> info dict of ref_driver."""
+    wmode = 1 if app == "sssp" else 0
+    cmd = [EXE, "--app", app, "--rmat", "%d,%d,%d,%d" % (scale, edgefactor, seed, wmode), "--source", "maxdeg",
+           "--repeat", str(int(repeat)), "--threads", str(int(threads)), "--opt", "1" if opt else "0"]
+    if out:
+        cmd += ["--out", out]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError("ref_driver failed (%d): %s" % (p.returncode, p.stderr[-2000:]))
+    return json.loads(p.stdout.strip().splitlines()[-1])
 
 
-def _rmat_file(scale, edgefactor, seed, weighted):
-    key = (scale, edgefactor, seed, weighted)
-    if key not in _graph_cache:
-        pkg = importlib.import_module("libgrape-lite_b200")
-        src, dst, w = pkg.rmat_edges_host(scale, edgefactor, seed, 1 if weighted else 0)
-        path = os.path.join(tempfile.gettempdir(), "grb_rmat_%d_%d_%d_%d.bin" % key)
-        write_graph(path, 1 << scale, src, dst, None if w is None else w.astype(np.float64))
-        deg = np.bincount(np.concatenate([src, dst]), minlength=1 << scale)
-        source = int(np.argmax(deg))      # max degree, ties -> smallest oid
-        _graph_cache.clear()
-        _graph_cache[key] = (path, source, len(src))
-    return _graph_cache[key]
-
-
-def run(exe, app, scale, edgefactor=16, seed=1, repeat=1, keep=1):
+def run(exe, app, scale, edgefactor=16, seed=1, repeat=1, keep=1, opt=False):
     """bench.py CPU arm: `repeat` queries of the reference CPU app in ONE process
-    (graph loaded once), all host threads; the mean of the last `keep` is reported."""
-    path, source, m = _rmat_file(scale, edgefactor, seed, app == "sssp")
-    info, text = run_app(app, path, source=source, repeat=repeat, want_output=(app in ("bfs", "sssp")))
+    (graph generated and loaded once), all host threads; the mean of the last `keep` is reported."""
+    info = run_rmat(app, scale, edgefactor, seed, repeat=repeat, opt=opt)
     ms = float(np.mean(info["query_ms"][-keep:]))
+    m = int(info["edges"])
     if app in ("bfs", "sssp"):
-        # Graph500 numerator: input edges with a reached endpoint
-        _, vals = parse_output(text, float if app == "sssp" else int)
-        reached = vals < 1e300 if app == "sssp" else vals != np.iinfo(np.int64).max
-        pkg = importlib.import_module("libgrape-lite_b200")
-        src, dst, _ = pkg.rmat_edges_host(scale, edgefactor, seed, 0)
-        edges = int(np.count_nonzero(reached[src]))
+        edges = int(info["traversed_edges"])     # Graph500 numerator: input edges with a reached source endpoint
     elif app in ("pagerank", "cdlp"):
         edges = m * 10
     else:
         edges = m
     return {"value": edges / (ms * 1e-3), "unit": "edges/s", "ms": ms, "cores": int(info["threads"]),
             "kind": "reference", "all_ms": [float(x) for x in info["query_ms"]], "load_s": info["load_s"],
-            "sample": "%s on R-MAT scale-%d (same generator/seed as the GPU arm), one Query() of the "
-                      "unmodified reference CPU app (ParallelEngine, %d threads of %d)"
-                      % (app.upper(), scale, info["threads"], info["hardware_concurrency"])}
+            "scale": scale, "opt": bool(opt), "source_oid": int(info["source"]), "traversed_edges": edges,
+            "sample": "%s on R-MAT scale-%d edgefactor-%d seed-%d (the GPU arm's generator, restated in "
+                      "oracle/rmat_gen.h), Query() of the unmodified reference CPU app%s (ParallelEngine, "
+                      "%d threads of %d)"
+                      % (app.upper(), scale, edgefactor, seed, " (--opt variant)" if opt else "",
+                         info["threads"], info["hardware_concurrency"])}

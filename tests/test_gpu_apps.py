@@ -38,8 +38,6 @@ def app_available(kind, frag, **cfg):
 def test_bfs_golden(p2p, directed, name, dopt, fuse):
     oids, und, dr = p2p
     frag = dr if directed else und
-    if directed and dopt:
-        pytest.skip("pull needs the transposed adjacency; covered by push")
     app = app_available("bfs", frag, source_oid=6, direction_opt=dopt, fuse_supersteps=fuse)
     app.query()
     depth = app.result()
@@ -65,6 +63,23 @@ def test_bfs_rmat_vs_oracle(scale, dopt, fuse):
         assert np.array_equal(app.result(), want)
         assert st.supersteps >= 2 and st.kernel_launches > 0
         app.close()
+    frag.close()
+
+
+@pytest.mark.parametrize("scale", [9, 21])
+def test_bfs_result_paths_agree(scale):
+    """gl_app_result for BFS: the default path (u8 depths over PCIe in chunks, widened to int64 by
+    host threads) and the plain int64 device array (cfg.reserved[6] = 1) return the same array."""
+    frag = pkg().Fragment.rmat(scale, 16, seed=3)
+    source, _ = frag.max_degree_vertex()
+    out = []
+    for flag in (0, 1):
+        app = app_available("bfs", frag, source_oid=int(source), reserved={6: flag})
+        app.query()
+        out.append(app.result())
+        app.close()
+    assert np.array_equal(out[0], out[1])
+    assert out[0][source] == 0 and np.any(out[0] == INT64_MAX)
     frag.close()
 
 
@@ -262,6 +277,72 @@ def test_pagerank_rmat_vs_oracle(pull):
     assert abs(got.sum() - 1.0) < (1e-6 if pull == 2 else 1e-9)
     assert st.supersteps == 12        # PEval + 10 updates + the final message round
     app.close()
+    frag.close()
+
+
+@pytest.mark.parametrize("pull", [0, 1])
+def test_pagerank_directed_golden(p2p, pull):
+    """p2p-31-PR-directed (misc/app_tests.sh PageRank on the directed load): push along out-edges;
+    pr_pull on a directed fragment falls back to push instead of gathering along out-edges."""
+    oids, _, dr = p2p
+    want = np.array([float(v) for _, v in G.golden_pairs("p2p-31-PR-directed")])
+    app = app_available("pagerank", dr, pr_delta=0.85, max_round=10, pr_pull=pull)
+    app.query()
+    got = app.result()
+    assert G.eps_check(got, want, 1e-4)
+    assert np.max(np.abs(got - want) / want) < 1e-6
+    app.close()
+
+
+@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("dopt", [0, 1])
+def test_bfs_directed_rmat_vs_oracle(dopt, fuse):
+    """Directed graph: push walks oe, the pull levels walk the real ie CSR (bfs.h:225-238)."""
+    scale = 15
+    n, src, dst, _ = rmat_graph(scale, seed=9)
+    g = pyoracle.Graph(n, src, dst, None, directed=True)
+    frag = pkg().Fragment.from_edges(n, src, dst, directed=True)
+    rp, _, _ = frag.csr(0)
+    source = int(np.argmax(np.diff(rp.astype(np.int64))))
+    app = app_available("bfs", frag, source_oid=source, direction_opt=dopt, fuse_supersteps=fuse)
+    st = app.query()
+    want, _ = g.bfs(source)
+    assert np.array_equal(app.result(), want)
+    if dopt:
+        assert any(st.step_mode[i] == 1 for i in range(st.n_steps))     # a pull level really ran
+    app.close()
+    frag.close()
+
+
+def test_directed_fragment_without_ie_is_safe():
+    """gl_frag_create with directed = 1 and no ie CSR (kOnlyOut): BFS must stay push-only (correct
+    levels), WCC must refuse instead of returning components of the out-edge graph."""
+    n, src, dst, _ = rmat_graph(12, seed=5)
+    g = pyoracle.Graph(n, src, dst, None, directed=True)
+    built = pkg().Fragment.from_edges(n, src, dst, directed=True)
+    rp, col, _ = built.csr(0)
+    built.close()
+    frag = pkg().Fragment.from_csr(n, rp, col, directed=True)          # only oe is passed
+    source = int(np.argmax(np.diff(rp.astype(np.int64))))
+    for fuse in (0, 1):
+        app = app_available("bfs", frag, source_oid=source, direction_opt=1, fuse_supersteps=fuse)
+        st = app.query()
+        assert np.array_equal(app.result(), g.bfs(source)[0])
+        assert all(st.step_mode[i] == 0 for i in range(st.n_steps))
+        app.close()
+    for kind in ("wcc", "wcc_opt"):
+        with pytest.raises(pkg().GrapeError):
+            pkg().App(kind, frag)
+    frag.close()
+
+
+def test_sssp_rejects_negative_weights():
+    n, src, dst, w = rmat_graph(8, seed=2, weight_mode=1)
+    w = w.copy()
+    w[3] = -1.0
+    frag = pkg().Fragment.from_edges(n, src, dst, w)
+    with pytest.raises(pkg().GrapeError):
+        pkg().App("sssp", frag, source_oid=0)
     frag.close()
 
 
