@@ -94,6 +94,217 @@ inline void ReportMemoryUsage(const std::string& marker) {
   VLOG(1) << marker << ", GPU memory used: " << (total_b - free_b) / 1048576.0 << " MB";
 }
 
+// ------------------------------------------------------- small utilities --
+// grape/cuda/utils/{array_view,cuda_utils(pinned_vector),device_buffer,event,
+// shared_array,sorted_search,markers}.h — same public names, new bodies.
+template <typename T>
+struct PinnedAllocator {   // page-locked host memory (cuda_utils.h pinned_vector)
+  using value_type = T;
+  PinnedAllocator() = default;
+  template <typename U>
+  PinnedAllocator(const PinnedAllocator<U>&) {}
+  T* allocate(size_t n) {
+    void* p = nullptr;
+    CHECK_CUDA(cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return static_cast<T*>(p);
+  }
+  void deallocate(T* p, size_t) { cudaFreeHost(p); }
+  template <typename U>
+  bool operator==(const PinnedAllocator<U>&) const { return true; }
+  template <typename U>
+  bool operator!=(const PinnedAllocator<U>&) const { return false; }
+};
+template <typename T>
+using pinned_vector = thrust::host_vector<T, PinnedAllocator<T>>;
+
+// array_view.h:23-67: non-owning (pointer, size) over device / pinned storage
+template <typename T>
+class ArrayView {
+ public:
+  ArrayView() = default;
+  explicit ArrayView(const thrust::device_vector<T>& v)
+      : data_(const_cast<T*>(thrust::raw_pointer_cast(v.data()))), size_(v.size()) {}
+  explicit ArrayView(const pinned_vector<T>& v)
+      : data_(const_cast<T*>(thrust::raw_pointer_cast(v.data()))), size_(v.size()) {}
+  DEV_HOST ArrayView(T* data, size_t size) : data_(data), size_(size) {}
+  DEV_HOST_INLINE T* data() { return data_; }
+  DEV_HOST_INLINE const T* data() const { return data_; }
+  DEV_HOST_INLINE size_t size() const { return size_; }
+  DEV_HOST_INLINE bool empty() const { return size_ == 0; }
+  DEV_INLINE T& operator[](size_t i) { return data_[i]; }
+  DEV_INLINE const T& operator[](size_t i) const { return data_[i]; }
+  DEV_INLINE void Swap(ArrayView<T>& rhs) {
+    T* d = data_;
+    data_ = rhs.data_;
+    rhs.data_ = d;
+    size_t n = size_;
+    size_ = rhs.size_;
+    rhs.size_ = n;
+  }
+  DEV_INLINE T* begin() { return data_; }
+  DEV_INLINE T* end() { return data_ + size_; }
+  DEV_INLINE const T* begin() const { return data_; }
+  DEV_INLINE const T* end() const { return data_ + size_; }
+
+ private:
+  T* data_ = nullptr;
+  size_t size_ = 0;
+};
+
+// device_buffer.h:28-92: grow-only device array (resize keeps the allocation)
+template <typename T>
+class DeviceBuffer {
+ public:
+  DeviceBuffer() = default;
+  explicit DeviceBuffer(size_t size) { resize(size); }
+  DeviceBuffer(const DeviceBuffer& rhs) { *this = rhs; }
+  DeviceBuffer(DeviceBuffer&& rhs) noexcept { *this = std::move(rhs); }
+  ~DeviceBuffer() {
+    if (data_) cudaFree(data_);
+  }
+  DeviceBuffer& operator=(const DeviceBuffer& rhs) {
+    if (&rhs != this) {
+      resize(rhs.size_);
+      if (size_) CHECK_CUDA(cudaMemcpy(data_, rhs.data_, sizeof(T) * size_, cudaMemcpyDeviceToDevice));
+    }
+    return *this;
+  }
+  DeviceBuffer& operator=(DeviceBuffer&& rhs) noexcept {
+    if (&rhs != this) {
+      if (data_) cudaFree(data_);
+      data_ = rhs.data_;
+      size_ = rhs.size_;
+      capacity_ = rhs.capacity_;
+      rhs.data_ = nullptr;
+      rhs.size_ = rhs.capacity_ = 0;
+    }
+    return *this;
+  }
+  void resize(size_t size) {
+    if (size > capacity_) {
+      T* n = nullptr;
+      CHECK_CUDA(cudaMalloc(&n, sizeof(T) * size));
+      if (size_) CHECK_CUDA(cudaMemcpy(n, data_, sizeof(T) * size_, cudaMemcpyDeviceToDevice));
+      if (data_) cudaFree(data_);
+      data_ = n;
+      capacity_ = size;
+    }
+    size_ = size;
+  }
+  T* data() { return data_; }
+  const T* data() const { return data_; }
+  size_t size() const { return size_; }
+  ArrayView<T> DeviceObject() { return ArrayView<T>(data_, size_); }
+
+ private:
+  T* data_ = nullptr;
+  size_t size_ = 0, capacity_ = 0;
+};
+
+// event.h:60-125: a recordable / waitable CUDA event with shared ownership
+class Event {
+ public:
+  Event() = default;
+  static Event Create() {
+    Event e;
+    cudaEvent_t ev;
+    CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e.ev_ = std::shared_ptr<CUevent_st>(ev, [](cudaEvent_t x) { cudaEventDestroy(x); });
+    return e;
+  }
+  void Record(const Stream& stream) const {
+    if (ev_) CHECK_CUDA(cudaEventRecord(ev_.get(), stream.cuda_stream()));
+  }
+  void Wait(const Stream& stream) const {
+    if (ev_) CHECK_CUDA(cudaStreamWaitEvent(stream.cuda_stream(), ev_.get(), 0));
+  }
+  void Sync() const {
+    if (ev_) CHECK_CUDA(cudaEventSynchronize(ev_.get()));
+  }
+  bool Query() const { return !ev_ || cudaEventQuery(ev_.get()) == cudaSuccess; }
+  cudaEvent_t cuda_event() const { return ev_.get(); }
+
+ private:
+  std::shared_ptr<CUevent_st> ev_;
+};
+
+// shared_array.h:24-140: a device array with a pinned host mirror
+template <typename T>
+class SharedArray {
+ public:
+  using device_t = thrust::device_vector<T>;
+  using host_t = pinned_vector<T>;
+  SharedArray() = default;
+  explicit SharedArray(size_t size) { resize(size); }
+  void resize(size_t size) {
+    d_.resize(size);
+    h_.resize(size);
+  }
+  size_t size() const { return d_.size(); }
+  void set(size_t idx, const T& t) { d_[idx] = t; }
+  void set(size_t idx, const T& t, const Stream& stream) {
+    h_[idx] = t;
+    CHECK_CUDA(cudaMemcpyAsync(data(idx), &h_[idx], sizeof(T), cudaMemcpyHostToDevice, stream.cuda_stream()));
+  }
+  void fill(const T& t) { thrust::fill(d_.begin(), d_.end(), t); }
+  void fill(const T& t, const Stream& stream) {
+    thrust::fill(thrust::cuda::par.on(stream.cuda_stream()), d_.begin(), d_.end(), t);
+  }
+  typename device_t::reference get(size_t idx) { return d_[idx]; }
+  typename device_t::const_reference get(size_t idx) const { return d_[idx]; }
+  T get(size_t idx, const Stream& stream) const {
+    T v;
+    CHECK_CUDA(cudaMemcpyAsync(&v, data(idx), sizeof(T), cudaMemcpyDeviceToHost, stream.cuda_stream()));
+    stream.Sync();
+    return v;
+  }
+  const host_t& get(const Stream& stream) const {
+    if (size()) {
+      CHECK_CUDA(cudaMemcpyAsync(const_cast<T*>(thrust::raw_pointer_cast(h_.data())), data(), sizeof(T) * size(),
+                                 cudaMemcpyDeviceToHost, stream.cuda_stream()));
+      stream.Sync();
+    }
+    return h_;
+  }
+  host_t& get(const Stream& stream) { return const_cast<host_t&>(static_cast<const SharedArray*>(this)->get(stream)); }
+  T* data() { return thrust::raw_pointer_cast(d_.data()); }
+  const T* data() const { return thrust::raw_pointer_cast(d_.data()); }
+  T* data(size_t idx) { return data() + idx; }
+  const T* data(size_t idx) const { return data() + idx; }
+  void Assign(const SharedArray<T>& rhs) {
+    d_ = rhs.d_;
+    h_.resize(d_.size());
+  }
+  void Assign(const SharedArray<T>& rhs, const Stream& stream) {
+    resize(rhs.size());
+    if (size()) CHECK_CUDA(cudaMemcpyAsync(data(), rhs.data(), sizeof(T) * size(), cudaMemcpyDeviceToDevice, stream.cuda_stream()));
+  }
+  void Swap(SharedArray<T>& rhs) {
+    d_.swap(rhs.d_);
+    h_.swap(rhs.h_);
+  }
+
+ private:
+  device_t d_;
+  mutable host_t h_;
+};
+
+// markers.h:25-190: NVTX ranges of the reference's PROFILING build.  The
+// profiling recipe here is ncu launch lists (profiles/), so a marker only keeps
+// its bookkeeping and nothing is emitted.
+class RangeMarker {
+ public:
+  explicit RangeMarker(bool start = false, const char* = nullptr, int = 0, int = 0) : running_(start) {}
+  explicit RangeMarker(const char*) {}
+  void Start() { running_ = true; }
+  void Stop() { running_ = false; }
+  bool running() const { return running_; }
+  static void MarkWorkitems(uint64_t, const char*) {}
+
+ private:
+  bool running_ = false;
+};
+
 // ------------------------------------------------------------- work source --
 // grape/cuda/utils/work_source.h:22-48
 template <typename T>
@@ -141,6 +352,23 @@ template <typename F, typename... Args>
 void LaunchKernelFix(const Stream& stream, size_t, F f, Args&&... args) {
   KernelWrapper<<<256, 256, 0, stream.cuda_stream()>>>(f, std::forward<Args>(args)...);
   CHECK_CUDA(cudaGetLastError());
+}
+
+// sorted_search.h:28-61: indices[i] = lower bound of needles[i] in the sorted haystack
+template <typename T>
+void sorted_search(const Stream& stream, T* needles, int num_needles, T* haystack, int num_haystack, T* indices) {
+  if (num_needles <= 0) return;
+  LaunchKernel(stream, (size_t) num_needles, [=] __device__() {
+    for (int i = TID_1D; i < num_needles; i += TOTAL_THREADS_1D) {
+      const T key = needles[i];
+      int lo = 0, hi = num_haystack;
+      while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (haystack[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      indices[i] = (T) lo;
+    }
+  });
 }
 
 // --------------------------------------------------------------- dev utils --
@@ -346,6 +574,77 @@ DEV_INLINE size_t intersect_num_blk(T* a, size_t size_a, T* b, size_t size_b, Y 
       }
     }
   return block_reduce(mine);
+}
+
+// Directed-LCC variants (dev_utils.h:696-892): a match a[i] == b[j] additionally
+// adds the per-entry weights of the OTHER list: *a_cnt += wb[j], *b_cnt += wa[i]
+// (the weights mark reciprocal edges, lcc_directed_opt.h:186-240).  On return
+// every lane / thread holds the warp / CTA totals.
+template <typename T>
+DEV_INLINE long long sorted_find(const T* a, size_t n, T key) {
+  size_t lo = 0, hi = n;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return (lo < n && a[lo] == key) ? (long long) lo : -1ll;
+}
+template <typename T, typename Y>
+DEV_INLINE void intersect_weighted(T* a, size_t size_a, T* b, size_t size_b, char* wa, size_t* a_cnt, char* wb,
+                                   size_t* b_cnt, Y callback, size_t first, size_t step) {
+  if (size_a == 0 || size_b == 0) return;
+  const bool swap = size_a > size_b;   // probe the shorter list into the longer one
+  const T* probe = swap ? b : a;
+  const T* hay = swap ? a : b;
+  const size_t np = swap ? size_b : size_a, nh = swap ? size_a : size_b;
+  for (size_t i = first; i < np; i += step) {
+    const T key = probe[i];
+    const long long j = sorted_find(hay, nh, key);
+    if (j >= 0) {
+      callback(key);
+      const size_t ia = swap ? (size_t) j : i, ib = swap ? i : (size_t) j;
+      *a_cnt += wb[ib];
+      *b_cnt += wa[ia];
+    }
+  }
+}
+template <typename T, typename Y>
+DEV_INLINE void intersect_num_d(T* a, size_t size_a, T* b, size_t size_b, char* wa, size_t* a_cnt, char* wb,
+                                size_t* b_cnt, Y callback) {
+  intersect_weighted(a, size_a, b, size_b, wa, a_cnt, wb, b_cnt, callback, threadIdx.x & 31, 32);
+  __syncwarp();
+  const size_t ra = warp_reduce(*a_cnt), rb = warp_reduce(*b_cnt);
+  *a_cnt = ra;
+  *b_cnt = rb;
+  __syncwarp();
+}
+template <typename T, typename Y>
+DEV_INLINE void intersect_num_blk_d(T* a, size_t size_a, T* b, size_t size_b, char* wa, size_t* a_cnt, char* wb,
+                                    size_t* b_cnt, Y callback) {
+  intersect_weighted(a, size_a, b, size_b, wa, a_cnt, wb, b_cnt, callback, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const size_t ra = block_reduce(*a_cnt);
+  const size_t rb = block_reduce(*b_cnt);
+  __syncthreads();
+  *a_cnt = ra;
+  *b_cnt = rb;
+}
+template <typename T>
+DEV_INLINE size_t intersect_num_directed(T* a, size_t size_a, T* b, size_t size_b, char* wb) {
+  size_t mine = 0;
+  if (size_a && size_b) {
+    const bool swap = size_a > size_b;
+    const T* probe = swap ? b : a;
+    const T* hay = swap ? a : b;
+    const size_t np = swap ? size_b : size_a, nh = swap ? size_a : size_b;
+    for (size_t i = threadIdx.x & 31; i < np; i += 32) {
+      const long long j = sorted_find(hay, nh, probe[i]);
+      if (j >= 0) mine += wb[swap ? i : (size_t) j];
+    }
+  }
+  const size_t total = warp_reduce(mine);
+  __syncwarp();
+  return total;
 }
 
 // Most-frequent-label counter of the CDLP app (dev_utils.h:384-470): an exact
@@ -717,6 +1016,134 @@ class Queue {
   SharedValue<SIZE_T> counter_;
 };
 
+// ------------------------------------------------------------ coo fragment --
+// grape/cuda/fragment/coo_fragment.h:29-107: the inner vertices' out-edges as a
+// flat (src, dst[, data]) list on the device (what wcc_opt.h iterates).
+namespace dev {
+template <typename OID_T, typename VID_T, typename VDATA_T, typename EDATA_T>
+class COOFragment {
+ public:
+  using oid_t = OID_T;
+  using vid_t = VID_T;
+  using vdata_t = VDATA_T;
+  using edata_t = EDATA_T;
+  using vertex_t = Vertex<vid_t>;
+  using edge_t = Edge<vid_t, EDATA_T>;
+  COOFragment() = default;
+  DEV_HOST COOFragment(ArrayView<edge_t> edges) : edges_(edges) {}
+  DEV_INLINE const edge_t& edge(size_t eid) const { return edges_[eid]; }
+  DEV_INLINE edge_t& edge(size_t eid) { return edges_[eid]; }
+  DEV_INLINE edge_t& operator[](size_t eid) const { return const_cast<ArrayView<edge_t>&>(edges_)[eid]; }
+  DEV_HOST_INLINE size_t GetEdgeNum() const { return edges_.size(); }
+
+ private:
+  ArrayView<edge_t> edges_;
+};
+}  // namespace dev
+template <typename OID_T, typename VID_T, typename VDATA_T, typename EDATA_T>
+class COOFragment {
+ public:
+  using oid_t = OID_T;
+  using vid_t = VID_T;
+  using vdata_t = VDATA_T;
+  using edata_t = EDATA_T;
+  using vertex_t = Vertex<VID_T>;
+  using edge_t = Edge<VID_T, EDATA_T>;
+  using device_t = dev::COOFragment<OID_T, VID_T, VDATA_T, EDATA_T>;
+  void Init(const thrust::host_vector<edge_t>& edges) { edges_ = edges; }
+  device_t DeviceObject() { return device_t(ArrayView<edge_t>(edges_)); }
+  size_t GetEdgeNum() const { return edges_.size(); }
+
+ private:
+  thrust::device_vector<edge_t> edges_;
+};
+
+// ------------------------------------------------------- device vertex map --
+// grape/cuda/vertex_map/device_vertex_map.h:33-172 on gl_vm_* (one oid array per
+// group + binary search; no hash chains).
+namespace dev {
+template <typename OID_T, typename VID_T>
+class DeviceVertexMap {
+ public:
+  DeviceVertexMap() { memset(&v_, 0, sizeof(v_)); }
+  explicit DeviceVertexMap(const gl_vm_view& v) : v_(v) {}
+  DEV_INLINE bool GetOid(const VID_T& gid, OID_T& oid) const {
+    return GetOid((fid_t) (gid >> v_.fid_offset), (VID_T) (gid & v_.id_mask), oid);
+  }
+  DEV_INLINE bool GetOid(fid_t fid, const VID_T& lid, OID_T& oid) const {
+    if (!v_.l2o || fid >= v_.fnum || lid >= v_.off[fid + 1] - v_.off[fid]) return false;
+    oid = (OID_T) v_.l2o[v_.off[fid] + lid];
+    return true;
+  }
+  DEV_INLINE bool GetGid(fid_t fid, const OID_T& oid, VID_T& gid) const {
+    if (!v_.l2o || fid >= v_.fnum) return false;
+    const int64_t* keys = (v_.sorted_oid ? v_.sorted_oid : v_.l2o) + v_.off[fid];
+    uint64_t lo = 0, hi = v_.off[fid + 1] - v_.off[fid];
+    const uint64_t n = hi;
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (keys[mid] < (int64_t) oid) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= n || keys[lo] != (int64_t) oid) return false;
+    const VID_T lid = v_.sorted_lid ? (VID_T) v_.sorted_lid[v_.off[fid] + lo] : (VID_T) lo;
+    gid = ((VID_T) fid << v_.fid_offset) | lid;
+    return true;
+  }
+  DEV_INLINE bool GetGid(const OID_T& oid, VID_T& gid) const {
+    for (fid_t f = 0; f < v_.fnum; ++f)
+      if (GetGid(f, oid, gid)) return true;
+    return false;
+  }
+  DEV_HOST_INLINE bool built() const { return v_.l2o != nullptr; }
+
+ private:
+  gl_vm_view v_;
+};
+}  // namespace dev
+template <typename HOST_VM_T>
+class DeviceVertexMap {
+  using OID_T = typename HOST_VM_T::oid_t;
+  using VID_T = typename HOST_VM_T::vid_t;
+
+ public:
+  DeviceVertexMap() = default;
+  ~DeviceVertexMap() {
+    if (vm_) gl_vm_destroy(vm_);
+  }
+  DeviceVertexMap(const DeviceVertexMap&) = delete;
+  DeviceVertexMap& operator=(const DeviceVertexMap&) = delete;
+  // :103-146: the host VertexMap's (fid, lid) -> oid tables go to the device
+  void Init(const Stream&, const CommSpec& comm_spec, std::unique_ptr<HOST_VM_T>& vm_ptr) {
+    const fid_t fnum = comm_spec.fnum();
+    std::vector<std::vector<int64_t>> oids(fnum);
+    std::vector<uint64_t> ivnums(fnum);
+    std::vector<const int64_t*> ptrs(fnum);
+    for (fid_t f = 0; f < fnum; ++f) {
+      const size_t n = vm_ptr->GetInnerVertexSize(f);
+      oids[f].resize(n);
+      for (size_t lid = 0; lid < n; ++lid) {
+        OID_T oid;
+        CHECK(vm_ptr->GetOid(f, (VID_T) lid, oid));
+        oids[f][lid] = (int64_t) oid;
+      }
+      ivnums[f] = n;
+      ptrs[f] = oids[f].data();
+    }
+    if (vm_) gl_vm_destroy(vm_);
+    CHECK_GL(gl_vm_create(&vm_, fnum, ivnums.data(), ptrs.data()));
+  }
+  dev::DeviceVertexMap<OID_T, VID_T> DeviceObject() const {
+    if (!vm_) return dev::DeviceVertexMap<OID_T, VID_T>();
+    gl_vm_view v;
+    CHECK_GL(gl_vm_view_get(vm_, &v));
+    return dev::DeviceVertexMap<OID_T, VID_T>(v);
+  }
+  gl_vm_t* handle() const { return vm_; }
+
+ private:
+  gl_vm_t* vm_ = nullptr;
+};
+
 // --------------------------------------------------------- device fragment --
 // grape/cuda/fragment/device_fragment.h:36-450 — accessors over the SoA view
 namespace dev {
@@ -796,6 +1223,7 @@ class DeviceFragment {
 
   DeviceFragment() = default;
   explicit DeviceFragment(const gl_frag_view& v) : v_(v) {}
+  DeviceFragment(const gl_frag_view& v, const DeviceVertexMap<OID_T, VID_T>& vm) : v_(v), vm_(vm) {}
 
   DEV_HOST_INLINE const gl_frag_view& view() const { return v_; }
   DEV_HOST_INLINE vertex_range_t Vertices() const { return vertex_range_t(0, v_.ivnum + v_.ovnum); }
@@ -890,13 +1318,39 @@ class DeviceFragment {
     const VID_T u = v.GetValue();
     return adj_list_t(v_.ie_col, (const EDATA_T*) v_.ie_w, v_.ie_split[u], v_.ie_rp[u + 1]);
   }
+  // device_fragment.h:64-172: oid <-> vertex; outer vertices and foreign gids need the
+  // device vertex map (apps that set need_build_device_vm)
   DEV_INLINE OID_T GetId(const vertex_t& v) const {
     const VID_T u = v.GetValue();
-    return v_.inner_oids ? (OID_T) v_.inner_oids[u] : (OID_T) (v_.oid_base + u);
+    if (u < v_.ivnum) return v_.inner_oids ? (OID_T) v_.inner_oids[u] : (OID_T) (v_.oid_base + u);
+    return Gid2Oid(GetOuterVertexGid(v));
   }
+  DEV_INLINE OID_T Gid2Oid(const VID_T& gid) const {
+    OID_T oid = OID_T();
+    bool ok = vm_.GetOid(gid, oid);
+    assert(ok);
+    (void) ok;
+    return oid;
+  }
+  DEV_INLINE bool Oid2Gid(const OID_T& oid, VID_T& gid) const { return vm_.GetGid(oid, gid); }
+  DEV_INLINE bool GetVertex(const OID_T& oid, vertex_t& v) const {
+    VID_T gid;
+    return vm_.GetGid(oid, gid) && Gid2Vertex(gid, v);
+  }
+  DEV_INLINE bool GetInnerVertex(const OID_T& oid, vertex_t& v) const {
+    VID_T gid;
+    return vm_.GetGid((fid_t) v_.fid, oid, gid) && InnerVertexGid2Vertex(gid, v);
+  }
+  DEV_INLINE bool GetOuterVertex(const OID_T& oid, vertex_t& v) const {
+    VID_T gid;
+    return vm_.GetGid(oid, gid) && OuterVertexGid2Vertex(gid, v);
+  }
+  DEV_INLINE OID_T GetInnerVertexId(const vertex_t& v) const { return GetId(v); }
+  DEV_INLINE OID_T GetOuterVertexId(const vertex_t& v) const { return Gid2Oid(GetOuterVertexGid(v)); }
 
  private:
   gl_frag_view v_;
+  DeviceVertexMap<OID_T, VID_T> vm_;
 };
 }  // namespace dev
 
@@ -932,6 +1386,8 @@ class HostFragment
   using inner_vertices_t = typename base_t::inner_vertices_t;
   using outer_vertices_t = typename base_t::outer_vertices_t;
   using device_t = dev::DeviceFragment<OID_T, VID_T, VDATA_T, EDATA_T, _load_strategy>;
+  using coo_t = COOFragment<OID_T, VID_T, VDATA_T, EDATA_T>;
+  using dev_vertex_map_t = cuda::DeviceVertexMap<VertexMap<OID_T, VID_T>>;
   using IsEdgeCut = std::true_type;
   using IsVertexCut = std::false_type;
   static constexpr grape::LoadStrategy load_strategy = _load_strategy;
@@ -956,13 +1412,35 @@ class HostFragment
 
   void PrepareToRunApp(const CommSpec& comm_spec, PrepareConf conf, const ParallelEngineSpec& pe_spec) {
     base_t::PrepareToRunApp(comm_spec, conf, pe_spec);
-    // split positions / outer ranges are part of the device layout already
+    // split positions / outer ranges are part of the device layout already;
+    // host_fragment.h:205-215: the device vertex map is built on request
+    if (conf.need_build_device_vm && !d_vm_) {
+      d_vm_ = std::make_shared<dev_vertex_map_t>();
+      Stream stream;
+      d_vm_->Init(stream, comm_spec, this->vm_ptr_);
+    }
   }
 
   device_t DeviceObject() const {
     gl_frag_view v;
     CHECK_GL(gl_frag_view_get(handle_, &v));
-    return device_t(v);
+    return d_vm_ ? device_t(v, d_vm_->DeviceObject()) : device_t(v);
+  }
+  // host_fragment.h:496-522: the inner vertices' out-edges as a device edge list.
+  // release_csr is accepted and ignored: the SoA CSR stays resident (the apps
+  // that convert keep using the fragment's id accessors).
+  std::shared_ptr<coo_t> ConvertToCOO(bool release_csr = false) {
+    (void) release_csr;
+    if (!coo_frag_) {
+      thrust::host_vector<typename coo_t::edge_t> edges;
+      edges.reserve(this->GetEdgeNum());
+      for (auto u : this->InnerVertices())
+        for (auto& e : this->GetOutgoingAdjList(u))
+          edges.push_back(typename coo_t::edge_t(u.GetValue(), e.get_neighbor().GetValue(), e.get_data()));
+      coo_frag_ = std::make_shared<coo_t>();
+      coo_frag_->Init(edges);
+    }
+    return coo_frag_;
   }
   gl_frag_t* handle() const { return handle_; }
   void OffloadTopology() const { CHECK_GL(gl_frag_offload(handle_)); }
@@ -1035,6 +1513,8 @@ class HostFragment
   }
 
   gl_frag_t* handle_ = nullptr;
+  std::shared_ptr<coo_t> coo_frag_;
+  std::shared_ptr<dev_vertex_map_t> d_vm_;
 };
 
 // ---------------------------------------------------------- message manager --

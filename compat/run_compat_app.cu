@@ -24,11 +24,16 @@
 #include "cuda/app_config.h"
 #include "cuda/bfs/bfs.h"
 #include "cuda/cdlp/cdlp.h"
+#include "cuda/lcc/lcc.h"
+#include "cuda/lcc/lcc_directed.h"
+#include "cuda/lcc/lcc_directed_opt.h"
+#include "cuda/lcc/lcc_directed_preprocess.h"
 #include "cuda/lcc/lcc_opt.h"
 #include "cuda/lcc/lcc_preprocess.h"
 #include "cuda/pagerank/pagerank.h"
 #include "cuda/sssp/sssp.h"
 #include "cuda/wcc/wcc.h"
+#include "cuda/wcc/wcc_opt.h"
 
 namespace gc = grape::cuda;
 
@@ -146,6 +151,9 @@ int main(int argc, char** argv) {
         rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kBothOutIn, gc::WCC>(comm_spec, o, app_config);
       else
         rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kOnlyOut, gc::WCC>(comm_spec, o, app_config);
+    } else if (a == "wcc_opt") {
+      // run_cuda_app.h:271-274 (COO fragment + union-find, gathered on fragment 0)
+      rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kOnlyOut, gc::WCCOpt>(comm_spec, o, app_config);
     } else if (a == "pagerank") {
       if (directed)
         rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kBothOutIn, gc::Pagerank>(comm_spec, o, app_config, std::stod(o["pr_d"]), std::stoi(o["pr_mr"]));
@@ -157,6 +165,20 @@ int main(int argc, char** argv) {
       size_t** row_offset = reinterpret_cast<size_t**>(malloc(sizeof(size_t*)));
       rc = CreateAndQueryWithPreprocess<grape::EmptyType, LoadStrategy::kOnlyOut, gc::LCCOPT, grape::LCCP>(
           comm_spec, o, app_config, col, row_offset);
+    } else if (a == "lcc" && directed) {
+      // run_cuda_app.h:290-299 (directed: LCCDOPT + the CPU preprocess LCCDP)
+      uint32_t** col = reinterpret_cast<uint32_t**>(malloc(sizeof(uint32_t*)));
+      size_t** row_offset = reinterpret_cast<size_t**>(malloc(sizeof(size_t*)));
+      char** weight = reinterpret_cast<char**>(malloc(sizeof(char*)));
+      size_t** true_degree = reinterpret_cast<size_t**>(malloc(sizeof(size_t*)));
+      rc = CreateAndQueryWithPreprocess<grape::EmptyType, LoadStrategy::kBothOutIn, gc::LCCDOPT, grape::LCCDP>(
+          comm_spec, o, app_config, col, row_offset, weight, true_degree);
+    } else if (a == "lcc_basic") {
+      // the non-"opt" GPU LCC apps (cuda/lcc/lcc.h, lcc_directed.h): message-driven neighbour exchange
+      if (directed)
+        rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kBothOutIn, gc::LCCD>(comm_spec, o, app_config);
+      else
+        rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kOnlyOut, gc::LCC>(comm_spec, o, app_config);
     } else if (a == "cdlp") {
       if (directed)
         rc = CreateAndQuery<grape::EmptyType, LoadStrategy::kBothOutIn, gc::CDLP>(comm_spec, o, app_config, std::stoi(o["cdlp_mr"]));

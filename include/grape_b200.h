@@ -194,10 +194,42 @@ int gl_frag_copy_ovgid(const gl_frag_t*, uint32_t* ovgid);
 int gl_frag_oid2lid(const gl_frag_t*, int64_t oid, uint32_t* lid);
 /* max-out-degree inner vertex (ties -> smallest lid) and its degree */
 int gl_frag_max_degree_vertex(const gl_frag_t*, uint32_t* lid, uint64_t* degree);
+/* Binary cache of a fragment: ImmutableEdgecutFragment::Serialize / Deserialize
+ * (grape/fragment/immutable_edgecut_fragment.h:508-584, immutable_csr.h:307-363;
+ * the reference writes <prefix>/frag_<fid>.s).  Header + raw SoA arrays; a load
+ * is fread + H2D, nothing is re-sorted. */
+int gl_frag_save(const gl_frag_t*, const char* path);
+int gl_frag_load(gl_frag_t** out, const char* path);
 /* OffloadTopology / ReloadTopology (host_fragment.h:440-468) */
 int gl_frag_offload(gl_frag_t*);
 int gl_frag_reload(gl_frag_t*);
 void gl_frag_destroy(gl_frag_t*);
+
+/* ------------------------------------------------------------------ *
+ * Device vertex map (oid <-> gid): replaces grape::cuda::DeviceVertexMap
+ * (grape/cuda/vertex_map/device_vertex_map.h:94-172; built when an app sets
+ * need_build_device_vm, host_fragment.h:205-215).  One device array of oids
+ * per group (fragment f at off[f]) + binary search instead of the reference's
+ * chained hash maps.  oids[f] = host array of fragment f's inner oids in lid
+ * order (VertexMap::GetOid(fid, lid)).
+ * ------------------------------------------------------------------ */
+typedef struct gl_vm gl_vm_t;
+typedef struct {
+  uint32_t fnum;
+  int fid_offset;
+  uint32_t id_mask;
+  const int64_t* l2o;          /* device [off[fnum]]: oid of (f, lid) at off[f] + lid   */
+  const uint64_t* off;         /* device [fnum+1]                                        */
+  const int64_t* sorted_oid;   /* device, NULL when every slice of l2o is ascending      */
+  const uint32_t* sorted_lid;  /* device, lid of sorted_oid[i]                           */
+} gl_vm_view;
+int gl_vm_create(gl_vm_t** out, uint32_t fnum, const uint64_t* ivnums, const int64_t* const* oids);
+int gl_vm_view_get(const gl_vm_t*, gl_vm_view* out);          /* DeviceObject()          */
+/* batch lookups on device arrays: dev::DeviceVertexMap::GetGid / GetOid (:36-80);
+ * unknown oid -> gid 0xFFFFFFFF, invalid gid -> oid -1 */
+int gl_vm_oid2gid(const gl_vm_t*, void* stream, const int64_t* d_oids, uint64_t n, uint32_t* d_gids);
+int gl_vm_gid2oid(const gl_vm_t*, void* stream, const uint32_t* d_gids, uint64_t n, int64_t* d_oids);
+void gl_vm_destroy(gl_vm_t*);
 
 /* ------------------------------------------------------------------ *
  * Fragment group communicator: replaces GPUMessageManager's NCCL/MPI
@@ -384,6 +416,11 @@ int gl_app_query(gl_app_t*, gl_query_stats* stats /* may be NULL */);
 /* Context::Output values for the inner vertices, in lid order, to HOST memory
  * (e.g. cuda/sssp/sssp.h:104-118).  elem: see gl_app_kind. */
 int gl_app_result(gl_app_t*, void* host_out, size_t bytes);
+/* WCC / CDLP keep labels as gids; with a vertex map attached, gl_app_result
+ * returns them as oids for ANY partition (without one: only for this library's
+ * contiguous-block builders, where gid -> oid is arithmetic or the fragment's
+ * own oid list).  The map is borrowed: keep it alive while the app is used. */
+int gl_app_set_vertex_map(gl_app_t*, const gl_vm_t* vm);
 /* oid of each inner vertex (first column of Output) */
 int gl_app_result_oids(gl_app_t*, int64_t* host_out, size_t count);
 void gl_app_destroy(gl_app_t*);

@@ -82,7 +82,8 @@ SYMBOLS = [
     "gl_last_error", "gl_abi_version", "gl_device_info", "gl_frag_create", "gl_frag_build_from_edges",
     "gl_frag_build_rmat", "gl_rmat_edges_host", "gl_frag_get_info", "gl_frag_view_get", "gl_frag_copy_csr",
     "gl_frag_copy_ovgid", "gl_frag_oid2lid", "gl_frag_max_degree_vertex", "gl_frag_offload",
-    "gl_frag_reload", "gl_frag_destroy", "gl_comm_create", "gl_comm_export", "gl_comm_open",
+    "gl_frag_reload", "gl_frag_destroy", "gl_frag_save", "gl_frag_load", "gl_vm_create", "gl_vm_view_get",
+    "gl_vm_oid2gid", "gl_vm_gid2oid", "gl_vm_destroy", "gl_app_set_vertex_map", "gl_comm_create", "gl_comm_export", "gl_comm_open",
     "gl_comm_destroy", "gl_comm_close_peers", "gl_comm_peer_write_us", "gl_mm_create", "gl_mm_init_buffer", "gl_mm_start",
     "gl_mm_start_round", "gl_mm_finish_round", "gl_mm_to_terminate", "gl_mm_force_continue", "gl_mm_view_get",
     "gl_mm_bytes_sent", "gl_mm_destroy", "gl_mm_process", "gl_mm_send_outer", "gl_allreduce", "gl_bitmap_create",
@@ -109,6 +110,7 @@ def lib():
         L.gl_kernel_launch_count.restype = C.c_uint64
         L.gl_mm_bytes_sent.restype = C.c_uint64
         L.gl_mm_destroy.restype = None
+        L.gl_vm_destroy.restype = None
         for f in ("gl_frag_destroy", "gl_comm_destroy", "gl_app_destroy", "gl_app_config_default"):
             getattr(L, f).restype = None
         _LIB = L
@@ -251,6 +253,16 @@ class Fragment:
         check(lib().gl_frag_max_degree_vertex(self.h, C.byref(lid), C.byref(deg)))
         return lid.value, deg.value
 
+    def save(self, path):
+        """Binary cache of the fragment (Serialize analogue)."""
+        check(lib().gl_frag_save(self.h, path.encode()))
+
+    @classmethod
+    def load(cls, path):
+        h = C.c_void_p()
+        check(lib().gl_frag_load(C.byref(h), path.encode()))
+        return cls(h)
+
     def offload(self):
         check(lib().gl_frag_offload(self.h))
 
@@ -308,6 +320,37 @@ class Comm:
     def close(self):
         if self.h:
             lib().gl_comm_destroy(self.h)
+            self.h = None
+
+
+class VertexMap:
+    """Device vertex map (oid <-> gid) of a fragment group: oid_lists[f] = inner oids of fragment f in lid order."""
+
+    def __init__(self, oid_lists):
+        self._keep = [np.ascontiguousarray(o, dtype=np.int64) for o in oid_lists]
+        n = len(self._keep)
+        iv = (C.c_uint64 * n)(*[len(o) for o in self._keep])
+        ptrs = (C.c_void_p * n)(*[o.ctypes.data if len(o) else None for o in self._keep])
+        self.h = C.c_void_p()
+        check(lib().gl_vm_create(C.byref(self.h), n, iv, ptrs))
+
+    def oid2gid(self, oids):
+        oids = np.ascontiguousarray(oids, dtype=np.int64)
+        d_in, d_out = DeviceArray(oids), DeviceArray(nbytes=4 * max(len(oids), 1))
+        check(lib().gl_vm_oid2gid(self.h, None, d_in.ptr, C.c_uint64(len(oids)), d_out.ptr))
+        check(lib().gl_dev_sync())
+        return d_out.download(np.uint32, len(oids))
+
+    def gid2oid(self, gids):
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        d_in, d_out = DeviceArray(gids), DeviceArray(nbytes=8 * max(len(gids), 1))
+        check(lib().gl_vm_gid2oid(self.h, None, d_in.ptr, C.c_uint64(len(gids)), d_out.ptr))
+        check(lib().gl_dev_sync())
+        return d_out.download(np.int64, len(gids))
+
+    def close(self):
+        if self.h:
+            lib().gl_vm_destroy(self.h)
             self.h = None
 
 
@@ -410,6 +453,10 @@ class App:
         self.h = C.c_void_p()
         check(lib().gl_app_create(C.byref(self.h), self.kind, frag.h, comm.h if comm else None, C.byref(c)))
         self.stats = QueryStats()
+
+    def set_vertex_map(self, vm):
+        self._vm = vm
+        check(lib().gl_app_set_vertex_map(self.h, vm.h if vm else None))
 
     def query(self):
         check(lib().gl_app_query(self.h, C.byref(self.stats)))

@@ -55,6 +55,7 @@ struct gl_app {
   // accumulated over one Query()
   uint64_t q_entries = 0, q_frontier = 0, q_touched = 0;
   int rounds = 0;
+  const gl_vm_t* vmap = nullptr;   // borrowed device vertex map (gl_app_set_vertex_map)
 
   virtual ~gl_app() {}
   virtual int Setup() = 0;                     // one-off allocations (GPUWorker::Init)

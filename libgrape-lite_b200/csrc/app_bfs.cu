@@ -25,6 +25,8 @@
 //    keep one launch group per superstep around the halo exchange.
 #include <cooperative_groups.h>
 
+#include <emmintrin.h>
+
 #include <thread>
 
 #include "apps_common.cuh"
@@ -1381,14 +1383,28 @@ struct BfsApp : gl_app {
       if (e > b) GL_CUDA(cudaMemcpyAsync(h_out8 + b, d_out8 + b, e - b, cudaMemcpyDeviceToHost, s));
       GL_CUDA(cudaEventRecord(ev8[c], s));
     }
-    static const int kThreads = std::max(1, std::min<int>(16, (int) std::thread::hardware_concurrency() / 2));
-    for (uint32_t c = 0; c < nchunks; ++c) {
-      const uint32_t b = std::min(n, c * per), e = std::min(n, b + per);
-      GL_CUDA(cudaEventSynchronize(ev8[c]));
-      const uint8_t* in = h_out8;
-#pragma omp parallel for num_threads(kThreads) schedule(static)
-      for (int64_t i = (int64_t) b; i < (int64_t) e; ++i) host_out[i] = in[i] == 0xFFu ? INT64_MAX : (int64_t) in[i];
+    // one team for the whole result: thread 0 waits for chunk c's copy, the team widens it with
+    // streaming stores (the int64 array is written once and not read back here) while chunk c+1
+    // is still crossing PCIe
+    static const int kThreads = std::max(1, std::min<int>(64, (int) std::thread::hardware_concurrency() / 2));
+    const uint8_t* in = h_out8;
+    cudaError_t err = cudaSuccess;
+#pragma omp parallel num_threads(kThreads)
+    {
+      for (uint32_t c = 0; c < nchunks; ++c) {
+        const int64_t b = std::min(n, c * per), e = std::min(n, (uint32_t) b + per);
+#pragma omp master
+        {
+          cudaError_t e1 = cudaEventSynchronize(ev8[c]);
+          if (e1 != cudaSuccess) err = e1;
+        }
+#pragma omp barrier
+#pragma omp for schedule(static) nowait
+        for (int64_t i = b; i < e; ++i)
+          _mm_stream_si64((long long*) (host_out + i), in[i] == 0xFFu ? (long long) INT64_MAX : (long long) in[i]);
+      }
     }
+    GL_CUDA(err);
     return GL_OK;
   }
 

@@ -56,6 +56,14 @@ __global__ void k_pr_dangling(const double* rank, const uint64_t* rp,
   if (lane_id() == 0 && s != 0.0) atomicAdd(out, s);
 }
 
+// Directed fragments follow the reference's directed app (pagerank_parallel.h:52-205, pinned by
+// dataset/p2p-31-PR-directed): a vertex WITHOUT out-edges keeps rank = base -- what arrives over
+// its in-edges is dropped -- so the dangling mass of a round is base * N_dangling.
+__global__ void k_pr_fix_dangling(double* rank, const uint64_t* rp, uint32_t ivnum, double base) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ivnum && rp[i + 1] == rp[i]) rank[i] = base;
+}
+
 __global__ void k_pr_base(double* next, uint32_t ivnum, double base) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < ivnum) next[i] = base;
@@ -162,6 +170,7 @@ struct PageRankApp : gl_app {
   size_t words = 0;
   uint32_t tvnum = 0;
   int curr_iter = 0;
+  double last_base = 0;
   // The pull sweep gathers along oe rows, which are the IN-neighbours only when
   // the fragment is undirected; on a directed fragment pr_pull falls back to the
   // push formulation (same ranks, pagerank.h:207-221), never a wrong gather.
@@ -266,6 +275,8 @@ struct PageRankApp : gl_app {
       PrApply ap{rank};
       GL_LAUNCH((k_unpack<ItemU32F64, PrApply>), eng.sm_count * 4, kTB, s, mv, ap, eng.ctrl);
     }
+    if (fv.directed && curr_iter > 0 && fv.ivnum)
+      GL_LAUNCH(k_pr_fix_dangling, (fv.ivnum + 255) / 256, 256, s, rank, fv.oe_rp, fv.ivnum, last_base);
     if (curr_iter++ >= cfg.max_round) return GL_OK;
     mm.ForceContinue();
     GL_TRY(eng.reset_ctrl());
@@ -278,6 +289,7 @@ struct PageRankApp : gl_app {
     GL_TRY(mm.AllReduceF64(&dangling, 1, 0));
     const double N = (double) fv.total_vnum;
     const double base = (1.0 - cfg.pr_delta) / N + cfg.pr_delta * dangling / N;
+    last_base = base;
     if (use_pull()) {
       if (cfg.reserved[5] == 1) GL_TRY(pull_sweep<float>(s, base));
       else GL_TRY(pull_sweep<double>(s, base));

@@ -97,21 +97,9 @@ struct WccApply {
   }
 };
 
-__global__ void k_wcc_out(const uint32_t* label, uint32_t n, int fid_offset,
-                          uint32_t id_mask, uint64_t chunk, uint32_t fnum,
-                          const int64_t* inner_oids, int64_t oid_base,
-                          int64_t* out) {
+__global__ void k_wcc_out(const uint32_t* label, uint32_t n, LabelMap lm, int64_t* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t g = label[i];
-  uint32_t f = g >> fid_offset, l = g & id_mask;
-  if (fnum == 1) {
-    out[i] = inner_oids ? inner_oids[l] : oid_base + (int64_t) l;
-  } else if (chunk && !inner_oids) {
-    out[i] = (int64_t) ((uint64_t) f * chunk + l);  // oid == global index
-  } else {
-    out[i] = (int64_t) g;  // no vertex map on the device: raw gid
-  }
+  if (i < n) out[i] = lm.oid(label[i]);
 }
 
 struct WccApp : gl_app {
@@ -215,8 +203,7 @@ struct WccApp : gl_app {
 
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
-    GL_LAUNCH(k_wcc_out, (fv.ivnum + 255) / 256, 256, eng.stream, label, fv.ivnum, fv.fid_offset,
-              fv.id_mask, frag->part_chunk, fv.fnum, fv.inner_oids, fv.oid_base, out64);
+    GL_LAUNCH(k_wcc_out, (fv.ivnum + 255) / 256, 256, eng.stream, label, fv.ivnum, label_map(*this), out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(int64_t) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
     GL_CUDA(cudaStreamSynchronize(eng.stream));
     return GL_OK;

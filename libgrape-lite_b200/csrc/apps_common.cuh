@@ -172,6 +172,29 @@ k_unpack(MsgView mv, Apply apply, ScanCtrl* ctrl) {
 }
 #endif
 
+// gid-valued label -> oid (WCC / CDLP outputs).  Without a vertex map the
+// mapping is exact only for this library's contiguous-block partition.
+struct LabelMap {
+  int fid_offset;
+  uint32_t id_mask, fnum;
+  uint64_t chunk;
+  const int64_t* inner_oids;
+  int64_t oid_base;
+  const int64_t* vm_l2o;    // device vertex map (gl_vm_*), or null
+  const uint64_t* vm_off;
+#ifdef __CUDACC__
+  GL_DEV int64_t oid(uint32_t g) const {
+    const uint32_t f = g >> fid_offset, l = g & id_mask;
+    if (vm_l2o) return vm_l2o[vm_off[f] + l];
+    if (fnum == 1) return inner_oids ? inner_oids[l] : oid_base + (int64_t) l;
+    if (chunk && !inner_oids) return (int64_t) ((uint64_t) f * chunk + l);   // oid == global index
+    return (int64_t) g;   // explicit oids, several fragments, no vertex map attached: raw gid
+  }
+#endif
+};
+
+LabelMap label_map(const gl_app& a);   // worker.cu
+
 struct ItemU32 {
   uint32_t lid;
 };

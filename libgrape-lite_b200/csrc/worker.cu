@@ -57,11 +57,45 @@ void StepRecorder::destroy() {
   ev.clear();
 }
 
+LabelMap label_map(const gl_app& a) {
+  LabelMap lm;
+  lm.fid_offset = a.fv.fid_offset;
+  lm.id_mask = a.fv.id_mask;
+  lm.fnum = a.fv.fnum;
+  lm.chunk = a.frag->part_chunk;
+  lm.inner_oids = a.fv.inner_oids;
+  lm.oid_base = a.fv.oid_base;
+  lm.vm_l2o = nullptr;
+  lm.vm_off = nullptr;
+  if (a.vmap) {
+    gl_vm_view v;
+    if (gl_vm_view_get(a.vmap, &v) == GL_OK && v.fnum == a.fv.fnum) {
+      lm.vm_l2o = v.l2o;
+      lm.vm_off = v.off;
+    }
+  }
+  return lm;
+}
+
 }  // namespace gl
 
 using namespace gl;
 
 extern "C" {
+
+int gl_app_set_vertex_map(gl_app_t* a, const gl_vm_t* vm) {
+  GL_ARG(a, "null argument");
+  if (vm) {
+    gl_vm_view v;
+    GL_TRY(gl_vm_view_get(vm, &v));
+    if (v.fnum != a->fv.fnum) {
+      set_error("gl_app_set_vertex_map: the map describes %u fragments, the app's fragment group has %u", v.fnum, a->fv.fnum);
+      return GL_ERR_ARG;
+    }
+  }
+  a->vmap = vm;
+  return GL_OK;
+}
 
 void gl_app_config_default(gl_app_config* c) {
   if (!c) return;

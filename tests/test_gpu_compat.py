@@ -160,3 +160,36 @@ def test_cdlp_multi_fragment(dataset, np_):
 def test_lcc_multi_fragment(dataset, np_):
     _, text = run(dataset, "lcc", "cm", np_=np_)
     assert text == G.golden_lines("p2p-31-LCC")
+
+
+# ---- the remaining dispatch targets of run_cuda_app.h:243-312 on the compat headers
+@pytest.mark.parametrize("np_", [1, 2, 3])
+def test_wcc_opt_unchanged_source(dataset, np_):
+    """cuda/wcc/wcc_opt.h (COOFragment via ConvertToCOO, ArrayView, pinned_vector, AllGather,
+    SendToFragmentWarpOpt, ParallelProcess of raw pairs; fragment 0 prints every vertex)."""
+    _, text = run(dataset, "wcc_opt", "cm", np_=np_)
+    got = np.array([int(l.split()[1]) for l in text.splitlines()])
+    want = np.array([int(v) for _, v in G.golden_pairs("p2p-31-WCC")])
+    assert len(got) == len(want) and G.same_partition(got, want)
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_lcc_basic_unchanged_source(dataset, np_):
+    """cuda/lcc/lcc.h, the message-driven (non-opt) GPU LCC: SendMsgThroughOEdges of degrees and
+    neighbour lists, ParallelProcess with Gid2Vertex on OUTER vertices, DropBuffer + a second InitBuffer."""
+    _, text = run(dataset, "lcc_basic", "cm", np_=np_)
+    assert text == G.golden_lines("p2p-31-LCC")
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_lcc_directed_variants_agree(dataset, np_):
+    """cuda/lcc/lcc_directed.h (device vertex map, intersect_num_directed) and lcc_directed_opt.h +
+    its CPU preprocess (intersect_num_d / _blk_d) are two implementations of directed LCC; the
+    reference ships no golden file for it, so they are checked against each other and across
+    fragment counts."""
+    _, a = run(dataset, "lcc", "cm", np_=np_, directed=1)
+    _, b = run(dataset, "lcc_basic", "cm", np_=np_, directed=1)
+    assert a == b
+    if np_ > 1:
+        _, c = run(dataset, "lcc", "cm", np_=1, directed=1)
+        assert a == c

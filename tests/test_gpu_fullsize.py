@@ -174,8 +174,8 @@ def test_scale20_against_the_reference_cpu_apps(app):
         assert np.max(np.abs(got - want) / want) < 1e-6
     elif app == "wcc":
         from tests import golden_io as G
-        assert G.same_partition(got, want)           # the CPU app labels classes by oid too: compare as partitions
-        assert np.array_equal(got, want)             # ... and here even the labels agree (min oid = min gid)
+        assert G.same_partition(got, want)           # misc/wcc_check.cc rule: labels in bijection
+        assert np.array_equal(got[got], got) and np.all(got <= np.arange(len(got)))   # label = smallest oid of the class
     elif app == "sssp":
         assert np.array_equal(got, want)             # integer weights: f32 on the GPU == f64 on the CPU
     else:
