@@ -811,7 +811,7 @@ class VertexArray {
   DEV_HOST VertexArray(T* data, VID_T begin, size_t size) : fake_(data - begin), size_(size) {}
   DEV_INLINE T& operator[](const Vertex<VID_T>& v) { return fake_[v.GetValue()]; }
   DEV_INLINE const T& operator[](const Vertex<VID_T>& v) const { return fake_[v.GetValue()]; }
-  DEV_INLINE T* data() { return fake_; }
+  DEV_HOST_INLINE T* data() { return fake_; }
   DEV_HOST_INLINE size_t size() const { return size_; }
 
  private:
@@ -1846,6 +1846,187 @@ class GPUMessageManager {
   Stream stream_;
   bool terminate_ = false;
   bool round_started_ = false;
+};
+
+// ------------------------------------------------- batch shuffle (dense sync) --
+// grape/cuda/parallel/batch_shuffle_message_manager.h:42-273,
+// grape/cuda/app/batch_shuffle_app_base.h:39-92,
+// grape/cuda/worker/gpu_batch_shuffle_worker.h:33-120: the message strategy in
+// which an owner pushes the state of ALL its mirrored inner vertices to the
+// fragments that hold copies.  On the C ABI's dense mirror sync
+// (gl_mm_mirror_plan / gl_mm_sync_values_to_ghosts): owners write straight into
+// the holders' mirror slots over NVLink, no ncclSend/ncclRecv staging buffers.
+class BatchShuffleMessageManager {
+ public:
+  BatchShuffleMessageManager() = default;
+  ~BatchShuffleMessageManager() { Release(); }
+  BatchShuffleMessageManager(const BatchShuffleMessageManager&) = delete;
+  BatchShuffleMessageManager& operator=(const BatchShuffleMessageManager&) = delete;
+
+  void Init(const grape::CommSpec& comm_spec) {
+    comm_spec_ = comm_spec;
+    fnum_ = comm_spec.fnum();
+    fid_ = comm_spec.fid();
+    CHECK_CUDA(cudaSetDevice(b200_pick_device(comm_spec.local_id())));
+  }
+  void Start() {}
+  void StartARound() {
+    to_terminate_ = true;
+    sent_size_ = 0;
+  }
+  void FinishARound() {}
+  void Finalize() const {}
+  // :142-220.  DATA_T must be 4 or 8 bytes wide (the C ABI's value sync).
+  template <typename GRAPH_T, typename DATA_T>
+  void SyncInnerVertices(const GRAPH_T& h_frag, VertexArray<DATA_T, typename GRAPH_T::vid_t>& h_data) {
+    static_assert(sizeof(DATA_T) == 4 || sizeof(DATA_T) == 8, "SyncInnerVertices: 4- or 8-byte vertex data");
+    to_terminate_ = false;
+    if (fnum_ == 1) return;
+    Ensure(h_frag);
+    auto d_data = h_data.DeviceObject();
+    CHECK_GL(gl_mm_sync_values_to_ghosts(mm_, stream_.cuda_stream(), (void*) d_data.data(), (int) sizeof(DATA_T)));
+    stream_.Sync();
+    sent_size_ += (size_t) h_frag.GetInnerVerticesNum() * sizeof(DATA_T);
+  }
+  bool ToTerminate() const { return to_terminate_; }
+  size_t GetMsgSize() const { return sent_size_; }
+  void ForceContinue() { to_terminate_ = false; }
+  Stream& stream() { return stream_; }
+  void* nccl_comm() { return nullptr; }
+  double GetAccumulatedCommTime() const { return 0.0; }
+
+ private:
+  static int HostAllReduce(void* user, void* inout, int n, int is_double, int op) {
+    auto* self = static_cast<BatchShuffleMessageManager*>(user);
+    const MPI_Op mop = op == 0 ? MPI_SUM : (op == 1 ? MPI_MIN : MPI_MAX);
+    return MPI_Allreduce(MPI_IN_PLACE, inout, n, is_double ? MPI_DOUBLE : MPI_INT64_T, mop, self->comm_spec_.comm());
+  }
+  template <typename GRAPH_T>
+  void Ensure(const GRAPH_T& h_frag) {
+    if (mm_) return;
+    unsigned long long iv = h_frag.GetInnerVerticesNum(), mx = 0;
+    MPI_Allreduce(&iv, &mx, 1, MPI_UNSIGNED_LONG_LONG, MPI_MAX, comm_spec_.comm());
+    gl_comm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.fid = fid_;
+    d.fnum = fnum_;
+    d.allreduce = &BatchShuffleMessageManager::HostAllReduce;
+    d.user = this;
+    d.landing_bytes = 4096;
+    d.mirror_bytes = (size_t) 8 * (mx + 1024);
+    CHECK_GL(gl_comm_create(&comm_, &d));
+    std::vector<char> mine(GL_IPC_HANDLE_BYTES), handles((size_t) GL_IPC_HANDLE_BYTES * fnum_);
+    CHECK_GL(gl_comm_export(comm_, mine.data(), mine.size()));
+    MPI_Allgather(mine.data(), GL_IPC_HANDLE_BYTES, MPI_CHAR, handles.data(), GL_IPC_HANDLE_BYTES, MPI_CHAR,
+                  comm_spec_.comm());
+    CHECK_GL(gl_comm_open(comm_, handles.data(), handles.size()));
+    CHECK_GL(gl_mm_create(&mm_, comm_));
+    MPI_Barrier(comm_spec_.comm());
+    CHECK_GL(gl_mm_mirror_plan(mm_, stream_.cuda_stream(), h_frag.handle()));
+  }
+  void Release() {
+    if (mm_) {
+      gl_mm_destroy(mm_);
+      mm_ = nullptr;
+    }
+    if (comm_) {
+      gl_comm_close_peers(comm_);
+      if (fnum_ > 1) MPI_Barrier(comm_spec_.comm());
+      gl_comm_destroy(comm_);
+      comm_ = nullptr;
+    }
+  }
+  grape::CommSpec comm_spec_;
+  fid_t fid_ = 0, fnum_ = 1;
+  gl_comm_t* comm_ = nullptr;
+  gl_mm_t* mm_ = nullptr;
+  Stream stream_;
+  size_t sent_size_ = 0;
+  bool to_terminate_ = false;
+};
+
+template <typename APP_T>
+class GPUBatchShuffleWorker;
+
+template <typename FRAG_T, typename CONTEXT_T>
+class BatchShuffleAppBase {
+ public:
+  static constexpr bool need_split_edges = false;
+  static constexpr bool need_build_device_vm = false;
+  static constexpr grape::MessageStrategy message_strategy = grape::MessageStrategy::kSyncOnOuterVertex;
+  static constexpr grape::LoadStrategy load_strategy = grape::LoadStrategy::kOnlyOut;
+  using message_manager_t = BatchShuffleMessageManager;
+  BatchShuffleAppBase() = default;
+  virtual ~BatchShuffleAppBase() = default;
+  virtual void PEval(const FRAG_T& graph, CONTEXT_T& context, message_manager_t& messages) = 0;
+  virtual void IncEval(const FRAG_T& graph, CONTEXT_T& context, message_manager_t& messages) = 0;
+};
+
+#define INSTALL_GPU_BATCH_SHUFFLE_WORKER(APP_T, CONTEXT_T, FRAG_T)   \
+ public:                                                             \
+  using fragment_t = FRAG_T;                                         \
+  using context_t = CONTEXT_T;                                       \
+  using worker_t = grape::cuda::GPUBatchShuffleWorker<APP_T>;        \
+  using message_manager_t = grape::cuda::BatchShuffleMessageManager; \
+  using dev_message_manager_t = grape::cuda::dev::MessageManager;    \
+  virtual ~APP_T() {}                                                \
+  static std::shared_ptr<worker_t> CreateWorker(                     \
+      std::shared_ptr<APP_T> app, std::shared_ptr<FRAG_T> frag) {    \
+    return std::shared_ptr<worker_t>(new worker_t(app, frag));       \
+  }
+
+template <typename APP_T>
+class GPUBatchShuffleWorker {
+ public:
+  using fragment_t = typename APP_T::fragment_t;
+  using context_t = typename APP_T::context_t;
+  using message_manager_t = BatchShuffleMessageManager;
+  GPUBatchShuffleWorker(std::shared_ptr<APP_T> app, std::shared_ptr<fragment_t> graph)
+      : app_(std::move(app)), context_(std::make_shared<context_t>(*graph)), messages_() {}
+  template <class... Args>
+  void Init(const grape::CommSpec& comm_spec, Args&&... args) {
+    auto& graph = const_cast<fragment_t&>(context_->fragment());
+    PrepareConf conf;
+    conf.message_strategy = APP_T::message_strategy;
+    conf.need_split_edges = APP_T::need_split_edges;
+    conf.need_split_edges_by_fragment = false;
+    conf.need_mirror_info = true;
+    conf.need_build_device_vm = APP_T::need_build_device_vm;
+    graph.PrepareToRunApp(comm_spec, conf, grape::DefaultParallelEngineSpec());
+    comm_spec_ = comm_spec;
+    messages_.Init(comm_spec);
+    InitCommunicator(app_, comm_spec.comm(), messages_.nccl_comm());
+    context_->Init(messages_, std::forward<Args>(args)...);
+  }
+  void Finalize() {}
+  void Query() {
+    auto& graph = context_->fragment();
+    messages_.Start();
+    messages_.StartARound();
+    app_->PEval(graph, *context_, messages_);
+    messages_.FinishARound();
+    MPI_Barrier(comm_spec_.comm());
+    int step = 1;
+    while (!messages_.ToTerminate()) {
+      messages_.StartARound();
+      app_->IncEval(graph, *context_, messages_);
+      messages_.FinishARound();
+      MPI_Barrier(comm_spec_.comm());
+      ++step;
+    }
+    supersteps_ = step;
+    messages_.Finalize();
+  }
+  int supersteps() const { return supersteps_; }
+  std::shared_ptr<context_t> GetContext() { return context_; }
+  void Output(std::ostream& os) { context_->Output(os); }
+
+ private:
+  std::shared_ptr<APP_T> app_;
+  std::shared_ptr<context_t> context_;
+  message_manager_t messages_;
+  grape::CommSpec comm_spec_;
+  int supersteps_ = 0;
 };
 
 // -------------------------------------------------------------- communicator --

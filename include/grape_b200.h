@@ -344,6 +344,21 @@ int gl_mm_process(gl_mm_t*, void* stream, const gl_msg_op* op, uint64_t* items_h
 int gl_mm_send_outer(gl_mm_t*, void* stream, const gl_frag_t* frag, uint32_t* remote_bitmap,
                      const void* state, int value_bytes, int clear_bits);
 
+/* Dense mirror sync: owner state -> the outer copies other fragments hold
+ * (BatchShuffleMessageManager::SyncInnerVertices,
+ * grape/cuda/parallel/batch_shuffle_message_manager.h:142-220; mirror lists =
+ * edgecut_fragment_base.h:569-603).  The communicator must have been created
+ * with mirror_bytes >= 8 * (largest inner vertex count of the group).
+ * gl_mm_mirror_plan is collective and runs once per (mm, fragment); every
+ * sync is collective: owners pack their mirrored values straight into the
+ * holders' mirror slots (peer stores), a device-side barrier follows, holders
+ * copy the slots into their outer range.  values: device array over ALL local
+ * vertices (inner then outer), elem_bytes 4 or 8; bitmap: one bit per local
+ * vertex (ghost bits |= owner bits). */
+int gl_mm_mirror_plan(gl_mm_t*, void* stream, const gl_frag_t* frag);
+int gl_mm_sync_values_to_ghosts(gl_mm_t*, void* stream, void* values, int elem_bytes);
+int gl_mm_sync_bits_to_ghosts(gl_mm_t*, void* stream, uint32_t* bitmap);
+
 /* cuda::Communicator::Sum/Min/Max on one host scalar
  * (grape/cuda/communication/communicator.h:41-84,160-172): device-side peer
  * all-reduce, bit-identical on every rank (fixed fid order).
@@ -383,6 +398,7 @@ typedef struct {
                             [1] 1: BFS without the hub-first shadow CSR
                             [2] BFS pull->push threshold divisor (default 24)
                             [3] >=4: number of BFS level bitmaps (forces spills)
+                            [4] 1: PageRank f32 pull without the shared-memory hub table (A/B)
                             [5] 1: PageRank pull gathers f32 contributions
                             [6] 1: BFS result as an int64 device array + one D2H
                                    (default: u8 depths over PCIe, widened on the host) */

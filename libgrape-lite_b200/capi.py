@@ -86,7 +86,8 @@ SYMBOLS = [
     "gl_vm_oid2gid", "gl_vm_gid2oid", "gl_vm_destroy", "gl_app_set_vertex_map", "gl_comm_create", "gl_comm_export", "gl_comm_open",
     "gl_comm_destroy", "gl_comm_close_peers", "gl_comm_peer_write_us", "gl_mm_create", "gl_mm_init_buffer", "gl_mm_start",
     "gl_mm_start_round", "gl_mm_finish_round", "gl_mm_to_terminate", "gl_mm_force_continue", "gl_mm_view_get",
-    "gl_mm_bytes_sent", "gl_mm_destroy", "gl_mm_process", "gl_mm_send_outer", "gl_allreduce", "gl_bitmap_create",
+    "gl_mm_bytes_sent", "gl_mm_destroy", "gl_mm_process", "gl_mm_send_outer", "gl_mm_mirror_plan", "gl_mm_sync_values_to_ghosts", "gl_mm_sync_bits_to_ghosts",
+    "gl_allreduce", "gl_bitmap_create",
     "gl_bitmap_clear", "gl_bitmap_count", "gl_bitmap_destroy", "gl_app_config_default", "gl_app_create", "gl_app_query", "gl_app_result",
     "gl_app_result_oids", "gl_app_destroy", "gl_edge_scan_queue", "gl_compact_bitmap", "gl_dev_alloc",
     "gl_dev_free", "gl_dev_memset", "gl_dev_h2d", "gl_dev_d2h", "gl_dev_sync", "gl_kernel_launch_count",

@@ -418,6 +418,7 @@ struct BfsFusedArgs {
   BfsFusedCtl* ctl;
   HubItem* hubs;
   uint32_t hub_cap, hub_deg;
+  int hub_tma;       // hub phase staged through the TMA engine (GL_HUB_TMA=0: plain loads)
 };
 
 // Level d reads lv[d] and writes lv[d+1] (pre-zeroed).  Every thread derives
@@ -426,9 +427,10 @@ struct BfsFusedArgs {
 // phase | hub phase).
 __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ union {
+  __shared__ __align__(128) union {
     ScanSmem<uint32_t> scan;
     PullSmem pull;
+    HubTmaSmem hub;
   } sm;
   __shared__ uint32_t s_item;
   BfsFusedCtl* ctl = a.ctl;
@@ -463,7 +465,8 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedAr
       OpBfsPush op{a.vis, nxt, nullptr, a.er.rp, a.pa.ivnum};
       frontier_scan_phase<OpBfsPush>(sm.scan, cur, a.pa.ivnum, a.er, op, C, a.hubs, a.hub_cap, a.hub_deg, acc);
       grid.sync();
-      hub_scan_phase<OpBfsPush>(&s_item, a.er, op, C, a.hubs, a.hub_cap, acc);
+      if (a.hub_tma) hub_scan_phase_tma<OpBfsPush>(sm.hub, a.er, op, C, a.hubs, a.hub_cap, acc);
+      else hub_scan_phase<OpBfsPush>(&s_item, a.er, op, C, a.hubs, a.hub_cap, acc);
     } else {
       bfs_pull_phase(sm.pull, a.pa, cur, a.vis, nxt, C, acc);
     }
@@ -714,11 +717,12 @@ struct BfsMultiArgs {
 
 __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsMultiArgs A) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ union {
+  __shared__ __align__(128) union {
     ScanSmem<uint32_t> scan;
     PullSmem pull;
     XSmem xs;
     PackSmem pack;
+    HubTmaSmem hub;
   } sm;
   __shared__ uint32_t s_item;
   const BfsFusedArgs& a = A.f;
@@ -783,7 +787,8 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
       GL_MARK(1);
       frontier_scan_phase<OpBfsPush>(sm.scan, cur, a.pa.ivnum, a.er, op, C, a.hubs, a.hub_cap, a.hub_deg, acc);
       grid.sync();
-      hub_scan_phase<OpBfsPush>(&s_item, a.er, op, C, a.hubs, a.hub_cap, acc);
+      if (a.hub_tma) hub_scan_phase_tma<OpBfsPush>(sm.hub, a.er, op, C, a.hubs, a.hub_cap, acc);
+      else hub_scan_phase<OpBfsPush>(&s_item, a.er, op, C, a.hubs, a.hub_cap, acc);
       flush_acc(acc, C);
       grid.sync();
       GL_MARK(2);
@@ -1142,6 +1147,7 @@ struct BfsApp : gl_app {
     a.hubs = eng.hubs;
     a.hub_cap = eng.hub_cap;
     a.hub_deg = eng.hub_deg;
+    a.hub_tma = (getenv("GL_HUB_TMA") && atoi(getenv("GL_HUB_TMA")) == 0) ? 0 : 1;
     const bool multi = fv.fnum > 1;
     if (!fused_grid)
       fused_grid = multi ? persistent_grid(k_bfs_fused_multi, eng.sm_count) : persistent_grid(k_bfs_fused, eng.sm_count);

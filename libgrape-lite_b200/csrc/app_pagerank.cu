@@ -123,6 +123,134 @@ __global__ void k_pr_permute_cols(const uint32_t* __restrict__ col, uint64_t m,
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Pull sweep with the hub contributions in shared memory.
+//
+// Why: ncu shows every formulation of the PageRank round (f64 atomics, f64 / f32
+// gathers) running at 70-90 G random accesses/s — the L1TEX divergent-request
+// rate (one 128-byte line per ~2 cycles per SM, B300_MICROARCH.md "LDG"), not
+// HBM.  Only shared memory serves 32 random lanes in a few cycles.  In the
+// hub-first id space (perm) the first kPrHub = 45056 contributions (176 KB of
+// f32) are the sources of ~43 % of all CSR entries of an R-MAT graph, so every
+// CTA keeps them in shared memory and only the remaining entries pay a global
+// (L2-resident, 67 MB) gather.  One CTA of 1024 threads per SM, column tiles
+// staged by the TMA engine (cp.async.bulk + mbarrier, double buffered).
+// ---------------------------------------------------------------------------
+constexpr int kPrTB = 1024;
+constexpr int kPrHub = 45056;                 // f32 contributions kept in shared memory (176 KB)
+constexpr int kPrEPT = kDenseTile / kPrTB;    // 4 consecutive entries per thread
+struct PrHubSmem {
+  float hub[kPrHub];
+  uint32_t col[2][kDenseTile];
+  uint64_t rp[kDenseRows + 2];
+  uint64_t bar[2];
+};
+
+__global__ void __launch_bounds__(kPrTB, 1)
+k_pr_pull_hub(const uint64_t* __restrict__ rp, const uint32_t* __restrict__ col_p,
+              const uint32_t* __restrict__ tile_row, uint32_t ntiles, uint32_t nrows, uint64_t m,
+              const float* __restrict__ contrib, uint32_t nhub, double* next, double delta, ScanCtrl* ctrl) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PrHubSmem& sm = *reinterpret_cast<PrHubSmem*>(smem_raw);
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    mbar_fence_init();
+  }
+  for (uint32_t i = threadIdx.x; i < nhub; i += kPrTB) sm.hub[i] = contrib[i];
+  __syncthreads();
+
+  auto issue = [&](uint32_t tile, int stage) {
+    const uint64_t e0 = (uint64_t) tile * kDenseTile;
+    const uint32_t n = (uint32_t) ((m - e0) < (uint64_t) kDenseTile ? (m - e0) : (uint64_t) kDenseTile);
+    const uint32_t bytes = ((n * 4u) + 15u) & ~15u;
+    mbar_expect_tx(&sm.bar[stage], bytes);
+    tma_load_1d(&sm.col[stage][0], col_p + e0, bytes, &sm.bar[stage]);
+  };
+
+  uint32_t it = 0;
+  uint32_t tile = blockIdx.x;
+  if (tile < ntiles && threadIdx.x == 0) issue(tile, 0);
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const uint32_t nexttile = tile + gridDim.x;
+    if (nexttile < ntiles && threadIdx.x == 0) issue(nexttile, stage ^ 1);
+    const uint64_t e0 = (uint64_t) tile * kDenseTile;
+    const uint32_t n = (uint32_t) ((m - e0) < (uint64_t) kDenseTile ? (m - e0) : (uint64_t) kDenseTile);
+    const uint32_t r0 = tile_row[tile];
+    uint32_t r1 = tile_row[tile + 1];
+    if (r1 >= nrows) r1 = nrows - 1;
+    const uint32_t nr = r1 - r0 + 1;
+    const bool fits = nr <= (uint32_t) kDenseRows;
+    if (fits)
+      for (uint32_t i = threadIdx.x; i <= nr; i += kPrTB) sm.rp[i] = rp[r0 + i];
+    __syncthreads();
+    mbar_wait_parity(&sm.bar[stage], (it >> 1) & 1);
+
+    const uint32_t le = threadIdx.x * kPrEPT;
+    const uint4 c = *(const uint4*) &sm.col[stage][le];
+    const uint32_t cs[4] = {c.x, c.y, c.z, c.w};
+    // global gathers first (in flight together), shared-memory hits afterwards
+    float gv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gv[k] = (le + k < n && cs[k] >= nhub) ? __ldcg(contrib + cs[k]) : 0.0f;
+    double ev[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ev[k] = (le + k < n) ? (double) (cs[k] < nhub ? sm.hub[cs[k]] : gv[k]) : 0.0;
+
+    uint32_t row = 0xFFFFFFFFu;
+    double part = 0.0;
+    if (le < n) {
+      const uint64_t e = e0 + le;
+      if (fits) {
+        uint32_t lo = 0, hi = nr + 1;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (sm.rp[mid] <= e) lo = mid + 1; else hi = mid;
+        }
+        row = r0 + lo - 1;
+      } else {
+        uint32_t lo = r0, hi = r1 + 2;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (rp[mid] <= e) lo = mid + 1; else hi = mid;
+        }
+        row = lo - 1;
+      }
+      uint64_t row_end = fits ? sm.rp[row - r0 + 1] : rp[row + 1];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (le + k < n) {
+          const uint64_t ek = e + k;
+          if (ek >= row_end) {
+            atomicAdd(next + row, delta * part);
+            part = 0.0;
+            do {
+              ++row;
+              row_end = fits ? sm.rp[row - r0 + 1] : rp[row + 1];
+            } while (ek >= row_end);
+          }
+          part += ev[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t orow = __shfl_up_sync(0xffffffffu, row, o);
+      const double oval = __shfl_up_sync(0xffffffffu, part, o);
+      if (lane_id() >= (uint32_t) o && orow == row) part += oval;
+    }
+    {
+      const uint32_t nrow = __shfl_down_sync(0xffffffffu, row, 1);
+      const bool tail = (lane_id() == 31) || (nrow != row);
+      if (tail && row != 0xFFFFFFFFu) atomicAdd(next + row, delta * part);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&ctrl->scanned, (unsigned long long) m);
+}
+
 __global__ void __launch_bounds__(kTB)
 k_pr_send(double* next, uint32_t ivnum, uint32_t ovnum,
           const uint32_t* __restrict__ ovgid, MsgView mv) {
@@ -258,7 +386,21 @@ struct PageRankApp : gl_app {
       GL_LAUNCH(k_pr_base, (fv.ivnum + 255) / 256, 256, s, next, fv.ivnum, base);
       static thread_local int gd = 0;
       if (!gd) gd = persistent_grid(k_dense_pull<OpPrPull<CT>>, eng.sm_count);
-      if (frag->oe_ntiles) {
+      if (frag->oe_ntiles && std::is_same<CT, float>::value && col_p && cfg.reserved[4] == 0) {
+        // hub-first gather order: the first kPrHub contributions live in shared memory
+        static thread_local int configured = 0;
+        if (!configured) {
+          GL_CUDA(cudaFuncSetAttribute(k_pr_pull_hub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(PrHubSmem)));
+          configured = 1;
+        }
+        const uint32_t nhub = std::min<uint32_t>((uint32_t) kPrHub, fv.ivnum);
+        const int grid = (int) std::min<uint32_t>((uint32_t) eng.sm_count, frag->oe_ntiles);
+        k_pr_pull_hub<<<grid, kPrTB, sizeof(PrHubSmem), s>>>(fv.oe_rp, col_p, frag->oe_tile_row, frag->oe_ntiles, fv.ivnum,
+                                                              (uint64_t) frag->oe.entries, (const float*) cb, nhub, next,
+                                                              cfg.pr_delta, eng.ctrl);
+        GL_COUNT_LAUNCH();
+        GL_CUDA(cudaGetLastError());
+      } else if (frag->oe_ntiles) {
         OpPrPull<CT> op{cb, next, cfg.pr_delta};
         int grid = (int) std::min<uint32_t>((uint32_t) gd, frag->oe_ntiles);
         GL_LAUNCH(k_dense_pull<OpPrPull<CT>>, grid, kTB, s, fv.oe_rp, col_p ? col_p : fv.oe_col, (const void*) nullptr,

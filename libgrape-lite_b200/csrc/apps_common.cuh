@@ -51,8 +51,15 @@ int run_frontier_scan(Engine& eng, const uint32_t* frontier, uint32_t nverts,
   int grid1 = (int) std::min<uint32_t>((uint32_t) g1, std::max<uint32_t>(ntiles, 1));
   GL_LAUNCH(k_frontier_scan<Op>, grid1, kTB, eng.stream, frontier, nverts, er,
             op, eng.ctrl, eng.hubs, eng.hub_cap, eng.hub_deg);
-  GL_LAUNCH(k_hub_scan<Op>, g2, kTB, eng.stream, er, op, eng.ctrl, eng.hubs,
-            eng.hub_cap);
+  // GL_HUB_TMA=0 selects the plain-load hub phase (A/B; profiles/r02_tma_hub_ab.txt)
+  static const bool tma = op_tma_ok<Op>::value && !(getenv("GL_HUB_TMA") && atoi(getenv("GL_HUB_TMA")) == 0);
+  if (tma) {
+    static thread_local int g3 = 0;
+    if (!g3) g3 = persistent_grid(k_hub_scan_tma<Op>, eng.sm_count);
+    GL_LAUNCH(k_hub_scan_tma<Op>, g3, kTB, eng.stream, er, op, eng.ctrl, eng.hubs, eng.hub_cap);
+  } else {
+    GL_LAUNCH(k_hub_scan<Op>, g2, kTB, eng.stream, er, op, eng.ctrl, eng.hubs, eng.hub_cap);
+  }
   return GL_OK;
 }
 

@@ -1,6 +1,7 @@
 // comm.cu — landing-area allocation / CUDA-IPC mapping and the round protocol.
 #include <cstring>
 #include "comm.h"
+#include "fragment.h"
 #include "engine.cuh"
 #include "apps_common.cuh"
 
@@ -1088,6 +1089,33 @@ int gl_mm_process(gl_mm_t* m, void* stream, const gl_msg_op* op, uint64_t* items
     *items_host = h;
   }
   return GL_OK;
+}
+
+int gl_mm_mirror_plan(gl_mm_t* m, void* stream, const gl_frag_t* frag) {
+  GL_ARG(m && frag, "null argument");
+  gl_frag_view fv;
+  frag_fill_view(frag, &fv);
+  if (fv.fnum != m->mm.fnum || fv.fid != m->mm.fid) {
+    set_error("gl_mm_mirror_plan: the fragment is not this rank's member of the group");
+    return GL_ERR_ARG;
+  }
+  return m->mm.BuildMirrorPlan((cudaStream_t) stream, fv);
+}
+int gl_mm_sync_values_to_ghosts(gl_mm_t* m, void* stream, void* values, int elem_bytes) {
+  GL_ARG(m && values && (elem_bytes == 4 || elem_bytes == 8), "gl_mm_sync_values_to_ghosts: bad argument");
+  if (m->mm.fnum > 1 && !m->mm.plan_built) {
+    set_error("gl_mm_sync_values_to_ghosts: call gl_mm_mirror_plan first");
+    return GL_ERR_STATE;
+  }
+  return m->mm.SyncValuesToGhosts((cudaStream_t) stream, values, elem_bytes);
+}
+int gl_mm_sync_bits_to_ghosts(gl_mm_t* m, void* stream, uint32_t* bitmap) {
+  GL_ARG(m && bitmap, "null argument");
+  if (m->mm.fnum > 1 && !m->mm.plan_built) {
+    set_error("gl_mm_sync_bits_to_ghosts: call gl_mm_mirror_plan first");
+    return GL_ERR_STATE;
+  }
+  return m->mm.SyncBitsToGhosts((cudaStream_t) stream, bitmap);
 }
 
 int gl_allreduce(gl_mm_t* m, void* stream, void* inout_host, int dtype, int op) {

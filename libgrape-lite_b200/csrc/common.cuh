@@ -147,6 +147,24 @@ GL_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+GL_DEV bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+GL_DEV void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-B aligned
 GL_DEV void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
                         uint64_t* bar) {

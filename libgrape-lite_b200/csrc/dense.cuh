@@ -34,24 +34,6 @@ struct DenseSmemW<void> {};
 
 #ifdef __CUDACC__
 
-GL_DEV bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-GL_DEV void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-
 // tile_row[t] = row containing entry t*kDenseTile (largest r with rp[r] <= e,
 // skipping empty rows); tile_row[ntiles] = nrows.
 static __global__ void k_dense_tile_rows(const uint64_t* __restrict__ rp, uint32_t nrows,

@@ -391,6 +391,73 @@ GL_DEV void hub_scan_phase(uint32_t* s_item, EdgeRange er, const Op& op,
     atomicAdd(&ctrl->scanned, (unsigned long long) scanned);
 }
 
+
+// Hub phase with the TMA engine staging the work items (north star: "TMA bulk
+// staging of CSR column-index tiles into shared memory"): the next item's
+// <= 1024 column indices (and f32 weights) stream into shared memory through
+// cp.async.bulk + mbarrier (SASS UBLKCP) while the CTA walks the current one.
+// Items start at arbitrary positions of a row: the copy starts at the enclosing
+// 16-byte boundary (col / w allocations are padded past their last entry).
+struct HubTmaSmem {
+  uint32_t col[2][kHubChunk + 16];
+  float w[2][kHubChunk + 16];
+  uint64_t bar[2];
+  uint32_t item[2];
+};
+
+template <class Op>
+GL_DEV void hub_scan_phase_tma(HubTmaSmem& sm, EdgeRange er, const Op& op, ScanCtrl* ctrl, const HubItem* hubs,
+                               uint32_t hub_cap, ScanAcc& acc) {
+  using W = typename Op::W;
+  static_assert(sizeof(W) == 4, "the staged weights are 4 bytes wide");
+  uint64_t scanned = 0;
+  uint32_t n = ctrl->hub_count;
+  if (n > hub_cap) n = hub_cap;
+  const bool with_w = Op::kWeighted && er.w != nullptr;
+  auto issue = [&](int stage, const HubItem& h) {
+    const uint64_t a = h.begin & ~3ull;
+    const uint32_t len = (uint32_t) (((h.end - a) + 3) & ~3ull);
+    const uint32_t bytes = len * 4u;
+    mbar_expect_tx(&sm.bar[stage], with_w ? 2u * bytes : bytes);
+    tma_load_1d(&sm.col[stage][0], er.col + a, bytes, &sm.bar[stage]);
+    if (with_w) tma_load_1d(&sm.w[stage][0], (const float*) er.w + a, bytes, &sm.bar[stage]);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    mbar_fence_init();
+    const uint32_t first = atomicAdd(&ctrl->hub_ticket, 1u);
+    sm.item[0] = first;
+    if (first < n) issue(0, hubs[first]);
+  }
+  __syncthreads();
+  for (uint32_t k = 0;; ++k) {
+    const int stage = (int) (k & 1);
+    const uint32_t cur = sm.item[stage];
+    if (cur >= n) break;   // uniform: read after a CTA barrier
+    if (threadIdx.x == 0) {
+      const uint32_t nxt = atomicAdd(&ctrl->hub_ticket, 1u);
+      sm.item[stage ^ 1] = nxt;
+      if (nxt < n) issue(stage ^ 1, hubs[nxt]);   // slot stage^1 was drained before the last barrier
+    }
+    const HubItem h = hubs[cur];
+    const auto meta = op.assign(h.v);
+    const uint64_t a = h.begin & ~3ull;
+    mbar_wait_parity(&sm.bar[stage], (k >> 1) & 1);
+    const uint32_t lo = (uint32_t) (h.begin - a), hi = (uint32_t) (h.end - a);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kTB) {
+      const uint32_t v = sm.col[stage][i];
+      W w = (W) 1;
+      if (with_w) w = (W) sm.w[stage][i];
+      call_edge(op, h.v, meta, v, w, a + i, acc);
+    }
+    if (threadIdx.x == 0) scanned += h.end - h.begin;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && scanned) atomicAdd(&ctrl->scanned, (unsigned long long) scanned);
+}
+
 template <class Op>
 __global__ void __launch_bounds__(kTB)
 k_frontier_scan(const uint32_t* __restrict__ frontier, uint32_t nverts,
@@ -402,6 +469,10 @@ k_frontier_scan(const uint32_t* __restrict__ frontier, uint32_t nverts,
   flush_acc(acc, ctrl);
 }
 
+// ops with 4-byte weights (or none) can take the TMA-staged hub phase
+template <class Op>
+struct op_tma_ok : std::integral_constant<bool, sizeof(typename Op::W) == 4> {};
+
 template <class Op>
 __global__ void __launch_bounds__(kTB)
 k_hub_scan(EdgeRange er, Op op, ScanCtrl* ctrl, const HubItem* hubs,
@@ -409,6 +480,15 @@ k_hub_scan(EdgeRange er, Op op, ScanCtrl* ctrl, const HubItem* hubs,
   __shared__ uint32_t s_item;
   ScanAcc acc;
   hub_scan_phase<Op>(&s_item, er, op, ctrl, hubs, hub_cap, acc);
+  flush_acc(acc, ctrl);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kTB)
+k_hub_scan_tma(EdgeRange er, Op op, ScanCtrl* ctrl, const HubItem* hubs, uint32_t hub_cap) {
+  __shared__ __align__(128) HubTmaSmem sm;
+  ScanAcc acc;
+  if constexpr (op_tma_ok<Op>::value) hub_scan_phase_tma<Op>(sm, er, op, ctrl, hubs, hub_cap, acc);
   flush_acc(acc, ctrl);
 }
 

@@ -414,15 +414,15 @@ int build_from_producer(gl_frag* f, Producer& prod, uint64_t n, int directed,
   GL_ALLOC(k_oe, sizeof(uint64_t) * m_oe);
   GL_ALLOC(k_oe2, sizeof(uint64_t) * m_oe);
   if (edata_bytes) {
-    GL_ALLOC(w_oe, (size_t) edata_bytes * m_oe);
-    GL_ALLOC(w_oe2, (size_t) edata_bytes * m_oe);
+    GL_ALLOC(w_oe, (size_t) edata_bytes * m_oe + 64);
+    GL_ALLOC(w_oe2, (size_t) edata_bytes * m_oe + 64);
   }
   if (directed) {
     GL_ALLOC(k_ie, sizeof(uint64_t) * m_ie);
     GL_ALLOC(k_ie2, sizeof(uint64_t) * m_ie);
     if (edata_bytes) {
-      GL_ALLOC(w_ie, (size_t) edata_bytes * m_ie);
-      GL_ALLOC(w_ie2, (size_t) edata_bytes * m_ie);
+      GL_ALLOC(w_ie, (size_t) edata_bytes * m_ie + 64);
+      GL_ALLOC(w_ie2, (size_t) edata_bytes * m_ie + 64);
     }
   }
   size_t ci = 0;
@@ -784,7 +784,7 @@ int gl_frag_create(gl_frag_t** out, const gl_frag_desc* d) {
     GL_CUDA(cudaMalloc(&o.col, sizeof(uint32_t) * (m + 16)));
     if (m) GL_CUDA(cudaMemcpy(o.col, c.col, sizeof(uint32_t) * m, cudaMemcpyHostToDevice));
     if (has_w && c.edata && m) {
-      GL_CUDA(cudaMalloc(&o.w, (size_t) d->edata_bytes * m));
+      GL_CUDA(cudaMalloc(&o.w, (size_t) d->edata_bytes * m + 64));   // +64: bulk copies round up to 16 bytes
       GL_CUDA(cudaMemcpy(o.w, c.edata, (size_t) d->edata_bytes * m, cudaMemcpyHostToDevice));
     }
     GL_CUDA(cudaMalloc(&o.split, sizeof(uint64_t) * std::max<uint64_t>(c.rows, 1)));
@@ -933,7 +933,7 @@ int gl_frag_reload(gl_frag_t* f) {
   GL_CUDA(cudaMalloc(&f->oe.col, sizeof(uint32_t) * (f->oe.entries + 16)));
   if (f->oe.entries) GL_CUDA(cudaMemcpy(f->oe.col, f->sh_col.data(), sizeof(uint32_t) * f->oe.entries, cudaMemcpyHostToDevice));
   if (!f->sh_w.empty()) {
-    GL_CUDA(cudaMalloc(&f->oe.w, f->sh_w.size()));
+    GL_CUDA(cudaMalloc(&f->oe.w, f->sh_w.size() + 64));
     GL_CUDA(cudaMemcpy(f->oe.w, f->sh_w.data(), f->sh_w.size(), cudaMemcpyHostToDevice));
   }
   if (f->ie_alias_oe) f->ie = f->oe;

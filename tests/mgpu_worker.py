@@ -151,6 +151,33 @@ def main():
             dist.barrier()
         comm.close()
         frag.close()
+    # WCC / CDLP on a fragment group with EXPLICIT oids: labels are gids internally; with the device
+    # vertex map attached (gl_vm_*, gl_app_set_vertex_map) the results come back as oids
+    scale2 = min(scale, 11)
+    n2 = 1 << scale2
+    oids = (np.arange(n2, dtype=np.int64) * 7 + 3)
+    src, dst, _ = pkg.rmat_edges_host(scale2, 16, 23, 0)
+    frag = pkg.Fragment.from_edges(n2, oids[src], oids[dst], None, oids=oids, fid=rank, fnum=world)
+    comm = gdist.make_comm(rank, world, frag.ivnum)
+    chunk = (n2 + world - 1) // world
+    vm = pkg.VertexMap([oids[f * chunk:(f + 1) * chunk] for f in range(world)])
+    g2 = pyoracle.Graph(n2, oids[src], oids[dst], None, oids=oids) if rank == 0 else None
+    for kind in ("wcc", "wcc_opt", "cdlp"):
+        app = pkg.App(kind, frag, comm, **({"max_round": 5} if kind == "cdlp" else {}))
+        app.set_vertex_map(vm)
+        app.query()
+        got = gather(app.result())
+        if rank == 0:
+            want = g2.cdlp(5) if kind == "cdlp" else oids[g2.wcc()[0].astype(np.int64)]
+            ok = np.array_equal(got, want)
+            print("[mgpu] %-13s fnum=%d scale=%d explicit oids + vertex map %s" % (kind + "_oids", world, scale2, "OK" if ok else "MISMATCH"), flush=True)
+            if not ok:
+                failures.append(kind + "_oids")
+        app.close()
+        dist.barrier()
+    vm.close()
+    comm.close()
+    frag.close()
     flag = torch.tensor([len(failures)], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

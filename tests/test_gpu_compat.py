@@ -193,3 +193,26 @@ def test_lcc_directed_variants_agree(dataset, np_):
     if np_ > 1:
         _, c = run(dataset, "lcc", "cm", np_=1, directed=1)
         assert a == c
+
+
+@pytest.mark.parametrize("np_", [1, 2, 3])
+def test_batch_shuffle_app_api(dataset, np_):
+    """BatchShuffleAppBase / GPUBatchShuffleWorker / BatchShuffleMessageManager::SyncInnerVertices
+    (dense owner -> mirror sync on gl_mm_mirror_plan + gl_mm_sync_values_to_ghosts): a pull PageRank
+    written on that API (compat/test_batch_shuffle.cu) reproduces p2p-31-PR on 1..3 fragments."""
+    exe = os.path.join(ROOT, "compat", "_build", "test_batch_shuffle")
+    if not os.path.exists(exe):
+        pytest.skip("compat/_build/test_batch_shuffle not built")
+    out = tempfile.mkdtemp()
+    env = dict(os.environ, GL_MPI_NP=str(np_), GL_MPI_TIMEOUT_S="300")
+    p = subprocess.run([exe, "--efile", os.path.join(dataset, "p2p-31.e"), "--vfile", os.path.join(dataset, "p2p-31.v"),
+                        "--out_prefix", out, "--pr_d", "0.85", "--pr_mr", "10"],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-2500:])
+    text = "".join(open(os.path.join(out, "result_frag_%d" % f)).read() for f in range(np_))
+    shutil.rmtree(out, ignore_errors=True)
+    rows = sorted((int(l.split()[0]), float(l.split()[1])) for l in text.splitlines())
+    got = np.array([v for _, v in rows])
+    want = np.array([float(v) for _, v in G.golden_pairs("p2p-31-PR")])
+    assert len(got) == len(want) and G.eps_check(got, want, 1e-4)
+    assert np.max(np.abs(got - want) / want) < 1e-6

@@ -111,3 +111,58 @@ def test_edge_cut_partition_layout(fnum):
         assert np.array_equal(np.diff(vrp).astype(np.int64), np.bincount(pairs[:, 0], minlength=f.ovnum))
         assert np.array_equal(vcol.astype(np.int64), pairs[:, 1])
         f.close()
+
+
+def test_fragment_save_load_roundtrip(tmp_path):
+    """gl_frag_save / gl_frag_load (Serialize / Deserialize analogue): every array of the reloaded
+    fragment equals the original, for weighted, directed and multi-fragment cases, and apps run on it."""
+    P = pkg()
+    n, src, dst, w = rmat_graph(11, seed=6, weight_mode=1)
+    oids = np.arange(n, dtype=np.int64) * 3 + 5
+    cases = [P.Fragment.rmat(11, 16, seed=6, weight_mode=1),
+             P.Fragment.from_edges(n, oids[src], oids[dst], w, oids=oids, directed=True),
+             P.Fragment.rmat(11, 16, seed=6, fid=1, fnum=3)]
+    for k, f in enumerate(cases):
+        path = str(tmp_path / ("frag_%d.bin" % k))
+        f.save(path)
+        g = P.Fragment.load(path)
+        assert (g.ivnum, g.ovnum, g.fid, g.fnum, g.oe_num, g.ie_num) == (f.ivnum, f.ovnum, f.fid, f.fnum, f.oe_num, f.ie_num)
+        for which in (0, 1, 2):
+            a, b = f.csr(which), g.csr(which)
+            for x, y in zip(a, b):
+                assert (x is None and y is None) or np.array_equal(x, y)
+        assert np.array_equal(f.ovgid(), g.ovgid())
+        if k < 2:
+            src_oid = int(oids[0]) if k == 1 else 0
+            ra, rb = [], []
+            for frag, out in ((f, ra), (g, rb)):
+                app = P.App("sssp", frag, source_oid=src_oid)
+                app.query()
+                out.append(app.result())
+                out.append(app.result_oids())
+                app.close()
+            assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+        g.close()
+        f.close()
+
+
+def test_device_vertex_map_lookups():
+    """gl_vm_*: oid <-> gid for ascending slices (binary search over l2o itself) and for
+    hash-partition style slices (sorted side index), unknown oids and invalid gids."""
+    P = pkg()
+    rng = np.random.default_rng(3)
+    all_oids = rng.choice(10**9, size=5000, replace=False).astype(np.int64)
+    for ascending in (True, False):
+        parts = np.array_split(all_oids, 3)
+        if ascending:
+            parts = [np.sort(p) for p in parts]
+        vm = P.VertexMap(parts)
+        gids = vm.oid2gid(all_oids)
+        off = 30   # fnum = 3 -> 2 fid bits
+        want = np.concatenate([(f << off) | np.arange(len(p)) for f, p in enumerate(parts)]).astype(np.uint32)
+        lookup = {int(o): int(g) for p_, f in zip(parts, range(3)) for o, g in zip(p_, ((f << off) | np.arange(len(p_))))}
+        assert np.array_equal(gids, np.array([lookup[int(o)] for o in all_oids], dtype=np.uint32))
+        assert np.array_equal(vm.gid2oid(want), np.concatenate(parts))
+        assert np.all(vm.oid2gid(np.array([-7, 10**12], dtype=np.int64)) == 0xFFFFFFFF)
+        assert np.all(vm.gid2oid(np.array([(2 << off) | 4999, 3 << off], dtype=np.uint32)) == -1)
+        vm.close()
