@@ -120,11 +120,20 @@ class Group:
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         if args.gpus != self.world and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+        # GL_ONE_DEVICE=1 (functional check of the N > 1 path on a 1-GPU box, never a measurement):
+        # every rank's fragment on cuda:0, contexts time-slice the GPU, rendezvous over gloo
+        self.one_device = os.environ.get("GL_ONE_DEVICE", "0") == "1"
+        if self.one_device:
+            self.local = 0
         torch.cuda.set_device(self.local)
         self.dist = None
+        self.tdev = "cpu" if self.one_device else "cuda"
         if self.world > 1:
             import torch.distributed as dist
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            if self.one_device:
+                dist.init_process_group("gloo")
+            else:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
 
     def barrier(self):
@@ -133,19 +142,19 @@ class Group:
         self.torch.cuda.synchronize()
 
     def reduce(self, vals, op="sum"):
-        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device=self.tdev)
         if self.dist:
             self.dist.all_reduce(t, op={"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX}[op])
         return [float(x) for x in t]
 
     def reduce_i64(self, vals, op="sum"):
-        t = self.torch.tensor(vals, dtype=self.torch.int64, device="cuda")
+        t = self.torch.tensor(vals, dtype=self.torch.int64, device=self.tdev)
         if self.dist:
             self.dist.all_reduce(t, op={"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX}[op])
         return [int(x) for x in t]
 
     def gather_i64(self, vals):
-        t = self.torch.tensor(vals, dtype=self.torch.int64, device="cuda")
+        t = self.torch.tensor(vals, dtype=self.torch.int64, device=self.tdev)
         if not self.dist:
             return [[int(x) for x in t]]
         allt = [self.torch.zeros_like(t) for _ in range(self.world)]
@@ -204,7 +213,7 @@ def measure_app(G, pkg, frag, comm, kind, cfg, steps, warmup, flush, edges_fn, w
     t_dev, launches, stats = 0.0, 0, []
     for _ in range(steps):
         flush.zero_()                      # L2 flush between timed iterations
-        torch.cuda.synchronize()
+        G.barrier()                        # ranks enter the query together (outside the event-timed interval)
         st = app.query()
         t_dev += st.query_ms
         launches += st.kernel_launches
@@ -429,6 +438,8 @@ def run_gpu(args):
         cfg["pr_pull"] = 1
         if args.pr_f32:
             cfg.setdefault("reserved", {})[5] = 1
+        if args.pr_nohub:
+            cfg.setdefault("reserved", {})[4] = 1
     kind = "wcc_opt" if (args.app == "wcc" and args.wcc_opt) else args.app
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     iters = 10 if args.app in ("pagerank", "cdlp") else 1
@@ -573,6 +584,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wcc-opt", action="store_true", help="WCC by union-find (the reference's wcc_opt) instead of label propagation")
     ap.add_argument("--pr-f32", action="store_true", help="PageRank pull gathering f32 contributions (f64 sums)")
+    ap.add_argument("--pr-nohub", action="store_true", help="with --pr-f32: without the shared-memory hub table (A/B)")
     ap.add_argument("--no-hub-order", action="store_true", help="disable the hub-first shadow CSR (BFS)")
     ap.add_argument("--bfs-beta", type=int, default=0, help="BFS pull->push threshold divisor (0 = library default)")
     ap.add_argument("--pr-pull", action="store_true", help="PageRank: deterministic pull step instead of atomicAdd push")

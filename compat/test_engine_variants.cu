@@ -31,6 +31,7 @@ struct Tester : public ParallelEngine {
     printf("%-32s %s (%zu items)\n", name, bad ? "MISMATCH" : "OK", n);
     failures += bad != 0;
     cudaMemset(d_out, 0, n * 8);
+    cudaDeviceSynchronize();   // the memset runs on the legacy stream, the kernels on a non-blocking one
   }
 
   void run() {
@@ -38,6 +39,7 @@ struct Tester : public ParallelEngine {
     WorkSourceRange<size_t> ws(7, n);
     unsigned long long* out = d_out;
     cudaMemset(d_out, 0, n * 8);
+    cudaDeviceSynchronize();
 
     ForEachWithIndexWarp(stream, ws, [=] __device__(size_t lane, size_t idx, size_t work) mutable {
       atomicAdd(out + idx, (unsigned long long) (work * 3 + lane));

@@ -157,7 +157,8 @@ typedef struct {
 int gl_frag_get_info(const gl_frag_t*, gl_frag_info* out);
 
 /* Device view (POD of device pointers): replaces HostFragment::DeviceObject()
- * (host_fragment.h:277-320).  Invalidated by offload/destroy. */
+ * (host_fragment.h:277-320).  Invalidated by destroy; while the topology is
+ * offloaded oe_col / oe_w (and their ie aliases) are NULL, the id fields stay valid. */
 typedef struct {
   uint32_t fid, fnum, ivnum, ovnum;
   uint64_t total_vnum;

@@ -25,9 +25,9 @@
 //    keep one launch group per superstep around the halo exchange.
 #include <cooperative_groups.h>
 
-#include <emmintrin.h>
-
 #include <thread>
+
+#include "host_pool.h"
 
 #include "apps_common.cuh"
 
@@ -1147,7 +1147,9 @@ struct BfsApp : gl_app {
     a.hubs = eng.hubs;
     a.hub_cap = eng.hub_cap;
     a.hub_deg = eng.hub_deg;
-    a.hub_tma = (getenv("GL_HUB_TMA") && atoi(getenv("GL_HUB_TMA")) == 0) ? 0 : 1;
+    // measured (profiles/r02_tma_hub_ab.txt): inside the fused kernel the TMA-staged hub phase is SLOWER
+    // (0.221 vs 0.179 ms per query) -- opt-in only; the stand-alone k_hub_scan_tma is the default elsewhere
+    a.hub_tma = (getenv("GL_HUB_TMA") && atoi(getenv("GL_HUB_TMA")) == 2) ? 1 : 0;
     const bool multi = fv.fnum > 1;
     if (!fused_grid)
       fused_grid = multi ? persistent_grid(k_bfs_fused_multi, eng.sm_count) : persistent_grid(k_bfs_fused, eng.sm_count);
@@ -1231,6 +1233,8 @@ struct BfsApp : gl_app {
     q_touched += h_ctl->touched;
     for (uint32_t i = 0; i < h_ctl->levels && i < (uint32_t) kMaxFusedStats; ++i)
       note_step(h_ctl->stat[i].scanned, h_ctl->stat[i].frontier, (int) h_ctl->stat[i].mode);
+    // every GPU left the kernel on the same all-reduced "frontier is empty": no round vote needed
+    mm.decided_terminate = true;
     return GL_OK;
   }
 
@@ -1389,27 +1393,15 @@ struct BfsApp : gl_app {
       if (e > b) GL_CUDA(cudaMemcpyAsync(h_out8 + b, d_out8 + b, e - b, cudaMemcpyDeviceToHost, s));
       GL_CUDA(cudaEventRecord(ev8[c], s));
     }
-    // one team for the whole result: thread 0 waits for chunk c's copy, the team widens it with
-    // streaming stores (the int64 array is written once and not read back here) while chunk c+1
-    // is still crossing PCIe
-    static const int kThreads = std::max(1, std::min<int>(64, (int) std::thread::hardware_concurrency() / 2));
-    const uint8_t* in = h_out8;
+    // host threads widen chunk c while chunk c+1 is still crossing PCIe (host_pool.h)
+    uint32_t bounds[9];
+    for (uint32_t c = 0; c <= nchunks; ++c) bounds[c] = std::min(n, c * per);
     cudaError_t err = cudaSuccess;
-#pragma omp parallel num_threads(kThreads)
-    {
-      for (uint32_t c = 0; c < nchunks; ++c) {
-        const int64_t b = std::min(n, c * per), e = std::min(n, (uint32_t) b + per);
-#pragma omp master
-        {
-          cudaError_t e1 = cudaEventSynchronize(ev8[c]);
-          if (e1 != cudaSuccess) err = e1;
-        }
-#pragma omp barrier
-#pragma omp for schedule(static) nowait
-        for (int64_t i = b; i < e; ++i)
-          _mm_stream_si64((long long*) (host_out + i), in[i] == 0xFFu ? (long long) INT64_MAX : (long long) in[i]);
-      }
-    }
+    WidenPool::instance().widen_u8_to_i64(h_out8, host_out, bounds, nchunks, [&](uint32_t c) {
+      cudaError_t e1 = cudaEventSynchronize(ev8[c]);
+      if (e1 != cudaSuccess) err = e1;
+    });
+    _mm_sfence();
     GL_CUDA(err);
     return GL_OK;
   }

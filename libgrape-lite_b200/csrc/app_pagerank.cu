@@ -378,6 +378,7 @@ struct PageRankApp : gl_app {
   template <typename CT>
   int pull_sweep(cudaStream_t s, double base) {
     CT* cb = (CT*) contrib;
+    l2_persist_window(s, cb, sizeof(CT) * (size_t) tvnum);   // the gathered array stays in L2, the CSR streams through
     if (fv.ivnum) GL_LAUNCH(k_pr_contrib<CT>, (fv.ivnum + 255) / 256, 256, s, rank, fv.oe_rp, fv.ivnum, perm, cb);
     // outer copies take their owner's contribution (dense mirror sync)
     if (fv.fnum > 1) GL_TRY(mm.SyncValuesToGhosts(s, cb, (int) sizeof(CT)));
@@ -437,6 +438,7 @@ struct PageRankApp : gl_app {
       else GL_TRY(pull_sweep<double>(s, base));
     } else {
       if (fv.ivnum) GL_LAUNCH(k_pr_base, (fv.ivnum + 255) / 256, 256, s, next, fv.ivnum, base);
+      l2_persist_window(s, next, sizeof(double) * (size_t) tvnum);   // atomics resolve in L2 as far as it can hold them
       OpPrPush op{rank, next, fv.oe_rp, cfg.pr_delta};
       EdgeRange er{fv.oe_rp, fv.oe_col, nullptr};
       GL_TRY(run_frontier_scan(eng, all_inner, fv.ivnum, er, op));
@@ -454,6 +456,7 @@ struct PageRankApp : gl_app {
 
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
+    l2_persist_clear(eng.stream);
     GL_CUDA(cudaMemcpyAsync(host_out, rank, sizeof(double) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
     GL_CUDA(cudaStreamSynchronize(eng.stream));
     return GL_OK;

@@ -205,6 +205,7 @@ struct SsspApp : gl_app {
     GL_CUDA(cudaMemsetAsync(remote, 0, sizeof(uint32_t) * words, s));
     prio = init_prio;
     far_total = 0;
+    l2_persist_window(s, dist, sizeof(T) * (size_t) tvnum);   // random dist[v] probes hit L2 while col / w stream through
     return GL_OK;
   }
 
@@ -260,6 +261,7 @@ struct SsspApp : gl_app {
 
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
+    l2_persist_clear(eng.stream);
     GL_LAUNCH(k_dist_to_f64<T>, (fv.ivnum + 255) / 256, 256, eng.stream, dist, fv.ivnum, inf(), out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(double) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
     GL_CUDA(cudaStreamSynchronize(eng.stream));

@@ -139,6 +139,7 @@ struct WccApp : gl_app {
     cudaStream_t s = eng.stream;
     GL_CUDA(cudaMemsetAsync(out_local, 0, sizeof(uint32_t) * words, s));
     GL_CUDA(cudaMemsetAsync(remote, 0, sizeof(uint32_t) * words, s));
+    l2_persist_window(s, label, sizeof(uint32_t) * (size_t) tvnum);   // random label[v] probes stay in L2
     return GL_OK;
   }
 
@@ -203,6 +204,7 @@ struct WccApp : gl_app {
 
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
+    l2_persist_clear(eng.stream);
     GL_LAUNCH(k_wcc_out, (fv.ivnum + 255) / 256, 256, eng.stream, label, fv.ivnum, label_map(*this), out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(int64_t) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
     GL_CUDA(cudaStreamSynchronize(eng.stream));

@@ -556,6 +556,11 @@ int MessageManager::StartARound(cudaStream_t s) {
 
 // publish counts -> sync -> all-reduce (barrier + termination vote)
 int MessageManager::FinishARound(cudaStream_t s) {
+  if (decided_terminate) {
+    decided_terminate = false;
+    terminate = true;
+    return GL_OK;
+  }
   int64_t vote[2] = {force_continue ? 1 : 0, 0};
   if (fnum > 1) {
     int par = round & 1;

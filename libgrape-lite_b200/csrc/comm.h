@@ -165,6 +165,10 @@ struct MessageManager {
   long long stat_in[2] = {0, 0};
   long long stat_out[2] = {0, 0};
   bool use_peer_barrier = true;
+  // set by an app whose PEval ran the whole query inside one kernel that already agreed on
+  // termination over its in-kernel collectives (fused BFS): the next FinishARound is then a
+  // local no-op on every rank instead of one more host-launched barrier + vote
+  bool decided_terminate = false;
   cudaStream_t stream_for_collectives = nullptr;
   unsigned long long seq = 0;
   PeerSlot** d_peer_slot[2] = {nullptr, nullptr};  // [parity][fnum] my slot at peer p

@@ -1,5 +1,7 @@
 // common.cu — error reporting, device probing and the small device-memory
 // helpers of the C ABI.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gl {
@@ -38,6 +40,60 @@ int device_info(DeviceInfo** out) {
     info.hbm_bytes = p.totalGlobalMem;
   }
   *out = &info;
+  return GL_OK;
+}
+
+namespace {
+struct L2Cfg {
+  int device = -1;
+  size_t persist_max = 0, window_max = 0;
+  bool enabled = true;
+};
+L2Cfg* l2cfg() {
+  static thread_local L2Cfg c;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (c.device != dev) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return nullptr;
+    c.device = dev;
+    c.persist_max = (size_t) p.persistingL2CacheMaxSize;
+    c.window_max = (size_t) p.accessPolicyMaxWindowSize;
+    const char* e = getenv("GL_L2_PERSIST");
+    c.enabled = !(e && atoi(e) == 0) && c.persist_max > 0 && c.window_max > 0;
+    if (c.enabled && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c.persist_max) != cudaSuccess) {
+      cudaGetLastError();
+      c.enabled = false;
+    }
+  }
+  return &c;
+}
+}  // namespace
+
+int l2_persist_window(cudaStream_t s, const void* ptr, size_t bytes) {
+  L2Cfg* c = l2cfg();
+  if (!c || !c->enabled || !ptr || !bytes) return GL_OK;
+  cudaStreamAttrValue a;
+  memset(&a, 0, sizeof(a));
+  a.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+  a.accessPolicyWindow.num_bytes = bytes < c->window_max ? bytes : c->window_max;
+  // the fraction of the window that may persist: what the set-aside can hold
+  double ratio = (double) c->persist_max * 0.95 / (double) a.accessPolicyWindow.num_bytes;
+  a.accessPolicyWindow.hitRatio = (float) (ratio > 1.0 ? 1.0 : ratio);
+  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
+  return GL_OK;
+}
+
+int l2_persist_clear(cudaStream_t s) {
+  L2Cfg* c = l2cfg();
+  if (!c || !c->enabled) return GL_OK;
+  cudaStreamAttrValue a;
+  memset(&a, 0, sizeof(a));
+  a.accessPolicyWindow.num_bytes = 0;
+  if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
+  cudaCtxResetPersistingL2Cache();
   return GL_OK;
 }
 

@@ -51,6 +51,14 @@ struct DeviceInfo {
 };
 int device_info(DeviceInfo** out);
 
+// L2 residency control (126 MB L2 on B200).  The randomly accessed per-vertex
+// state of a sweep (PageRank contributions, SSSP distances, WCC labels: 64-128 MB
+// at 2^24 vertices) competes with the streamed CSR (2-4 GB per sweep) for the L2;
+// an access-policy window marks the state as PERSISTING and everything else the
+// stream's kernels touch as STREAMING.  GL_L2_PERSIST=0 disables it (A/B).
+int l2_persist_window(cudaStream_t s, const void* ptr, size_t bytes);
+int l2_persist_clear(cudaStream_t s);
+
 // Kernel launch counter (gpu_launches claim in bench.py)
 extern thread_local uint64_t g_kernel_launches;
 #define GL_COUNT_LAUNCH() (++::gl::g_kernel_launches)

@@ -847,10 +847,9 @@ int gl_frag_get_info(const gl_frag_t* f, gl_frag_info* o) {
 
 int gl_frag_view_get(const gl_frag_t* f, gl_frag_view* v) {
   GL_ARG(f && v, "null argument");
-  if (f->offloaded) {
-    set_error("fragment topology is offloaded");
-    return GL_ERR_STATE;
-  }
+  // While the topology is offloaded (OffloadTopology, host_fragment.h:440-455) the view stays
+  // usable for everything that is not adjacency: ids, gids of outer copies, ranges -- the
+  // reference's lcc.h keeps calling DeviceObject() after it offloaded.  oe_col / oe_w are NULL.
   frag_fill_view(f, v);
   return GL_OK;
 }
