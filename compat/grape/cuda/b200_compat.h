@@ -1571,8 +1571,12 @@ class InArchive {
 
 class MessageManager {
  public:
-  MessageManager() { memset(&mv_, 0, sizeof(mv_)); }
-  explicit MessageManager(const gl_mm_view& mv) : mv_(mv) {}
+  // The object holds a pointer to a DEVICE-resident gl_mm_view that the host side refreshes
+  // whenever the slots change (every StartARound, every InitBuffer): like the reference's
+  // ArrayView over d_to_send_ (gpu_message_manager.h:342-344), a DeviceObject() taken before a
+  // re-InitBuffer in the same round (lcc.h:392 vs :416) keeps working.
+  MessageManager() = default;
+  explicit MessageManager(const gl_mm_view* d_view) : mvp_(d_view) {}
 
   // (gid of the outer vertex, msg) to the vertex's owner (:53-82)
   template <typename GRAPH_T, typename MESSAGE_T>
@@ -1624,14 +1628,15 @@ class MessageManager {
   DEV_INLINE void SendToFragmentWarpOpt(fid_t dst_fid, const MESSAGE_T& msg) {
     warp_opt(dst_fid, msg);
   }
-  DEV_HOST_INLINE const gl_mm_view& view() const { return mv_; }
 
  private:
   DEV_INLINE InArchive archive(fid_t f) const {
+    const gl_mm_view& mv_ = *mvp_;
     return InArchive(mv_.send_slot[f], mv_.send_bytes + f, mv_.capacity_bytes);
   }
   template <typename T>
   DEV_INLINE void warp_opt(fid_t f, const T& item) const {
+    const gl_mm_view& mv_ = *mvp_;
     const uint32_t active = __activemask();
     const uint32_t peers = __match_any_sync(active, f);
     const uint32_t leader = __ffs(peers) - 1;
@@ -1663,7 +1668,7 @@ class MessageManager {
       archive(f).AddBytes(item);
     }
   }
-  gl_mm_view mv_;
+  const gl_mm_view* mvp_ = nullptr;
 };
 
 // message_kernels.h:28-127 ProcessMsg: apply func to every received unit
@@ -1715,7 +1720,10 @@ __global__ void ProcessRawMsg(gl_mm_view mv, FUNC_T func) {
 class GPUMessageManager {
  public:
   GPUMessageManager() = default;
-  ~GPUMessageManager() { Release(false); }
+  ~GPUMessageManager() {
+    Release(false);
+    if (d_view_) cudaFree(d_view_);
+  }
   GPUMessageManager(const GPUMessageManager&) = delete;
   GPUMessageManager& operator=(const GPUMessageManager&) = delete;
 
@@ -1756,16 +1764,24 @@ class GPUMessageManager {
     CHECK_GL(gl_mm_init_buffer(mm_, send_buffer_capacity, recv_buffer_capacity));
     capacity_ = all;
     MPI_Barrier(comm_spec_.comm());   // every landing area is mapped before the first round
+    // a re-InitBuffer in the middle of a round (lcc.h:416): the new manager joins the round in progress
+    if (round_started_) CHECK_GL(gl_mm_start_round(mm_, stream_.cuda_stream()));
+    if (force_continue_) CHECK_GL(gl_mm_force_continue(mm_));
+    RefreshDeviceView();
   }
   void DropBuffer() { Release(true); }
 
   void Start() {
     if (mm_) CHECK_GL(gl_mm_start(mm_));
     round_started_ = false;
+    force_continue_ = false;
   }
   void StartARound() {
     EnsureManager();
     CHECK_GL(gl_mm_start_round(mm_, stream_.cuda_stream()));
+    round_started_ = true;
+    force_continue_ = false;
+    RefreshDeviceView();
   }
   void FinishARound() {
     EnsureManager();
@@ -1773,12 +1789,14 @@ class GPUMessageManager {
     int t = 0;
     CHECK_GL(gl_mm_to_terminate(mm_, &t));
     terminate_ = t != 0;
+    round_started_ = false;
   }
   void Finalize() const {}
   bool ToTerminate() const { return terminate_; }
   void ForceContinue() {
     EnsureManager();
     CHECK_GL(gl_mm_force_continue(mm_));
+    force_continue_ = true;
   }
   size_t GetMsgSize() const { return mm_ ? (size_t) gl_mm_bytes_sent(mm_) : 0; }
   double GetAccumulatedCommTime() const { return 0.0; }
@@ -1787,9 +1805,8 @@ class GPUMessageManager {
   gl_mm_t* handle() const { return mm_; }
   dev::MessageManager DeviceObject() {
     EnsureManager();
-    gl_mm_view mv;
-    CHECK_GL(gl_mm_view_get(mm_, &mv));
-    return dev::MessageManager(mv);
+    if (!d_view_) RefreshDeviceView();
+    return dev::MessageManager(d_view_);
   }
   // :362-393
   template <typename GRAPH_T, typename MESSAGE_T = grape::EmptyType, typename FUNC_T>
@@ -1821,6 +1838,14 @@ class GPUMessageManager {
     // an app that never called InitBuffer still gets a working round protocol
     if (!mm_) InitBuffer(4096, 4096);
   }
+  void RefreshDeviceView() {
+    if (!mm_) return;
+    if (!d_view_) CHECK_CUDA(cudaMalloc(&d_view_, sizeof(gl_mm_view)));
+    gl_mm_view mv;
+    CHECK_GL(gl_mm_view_get(mm_, &mv));
+    CHECK_CUDA(cudaMemcpyAsync(d_view_, &mv, sizeof(mv), cudaMemcpyHostToDevice, stream_.cuda_stream()));
+    stream_.Sync();
+  }
   void Release(bool collective) {
     if (mm_) {
       stream_.Sync();
@@ -1846,6 +1871,8 @@ class GPUMessageManager {
   Stream stream_;
   bool terminate_ = false;
   bool round_started_ = false;
+  bool force_continue_ = false;
+  gl_mm_view* d_view_ = nullptr;
 };
 
 // ------------------------------------------------- batch shuffle (dense sync) --

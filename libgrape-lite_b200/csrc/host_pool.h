@@ -60,9 +60,11 @@ class WidenPool {
     if (hw == 0) hw = 8;
     unsigned local = 1;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) local = (unsigned) std::max(1, atoi(e));
-    unsigned k = hw / (2 * local);
+    // measured on the 128-thread host of the GPU box: a streaming-store thread sustains only
+    // ~1.7 GB/s into the pinned result buffer, so the conversion scales with the thread count
+    unsigned k = hw * 3 / (4 * local);
     if (const char* e = getenv("GL_HOST_THREADS")) k = (unsigned) std::max(1, atoi(e));
-    k = std::max(1u, std::min(32u, k));
+    k = std::max(1u, std::min(96u, k));
     for (unsigned i = 0; i + 1 < k; ++i) th_.emplace_back([this, i] { loop((int) i); });
   }
   ~WidenPool() {
