@@ -219,7 +219,8 @@ int main(int argc, char** argv) {
                                           {"out_prefix", ""},     {"directed", "0"}, {"bfs_source", "0"},
                                           {"sssp_source", "0"},   {"pr_d", "0.85"},  {"pr_mr", "10"},
                                           {"lb", "cta"},          {"cdlp_mr", "10"},
-                                          {"rmat", ""},           {"repeat", "1"}};
+                                          {"rmat", ""},           {"repeat", "1"},
+                                          {"wl_in", "0.4"},       {"wl_out_local", "0.2"}, {"wl_out_remote", "0.2"}};
   for (int i = 1; i + 1 < argc; i += 2) {
     std::string k = argv[i];
     if (k.rfind("--", 0) != 0 || !o.count(k.substr(2))) {
@@ -236,9 +237,11 @@ int main(int argc, char** argv) {
     // run_cuda_app.h:235-240
     gc::AppConfig app_config;
     app_config.lb = gc::ParseLoadBalancing(split_list(o["lb"]).empty() ? std::string("cta") : split_list(o["lb"])[0]);
-    app_config.wl_alloc_factor_in = 0.4;
-    app_config.wl_alloc_factor_out_local = 0.2;
-    app_config.wl_alloc_factor_out_remote = 0.2;
+    // flags.cc:64-69 defaults; a frontier of an R-MAT graph can exceed 40 % of the vertices, which overflows
+    // the reference's work lists (its BFS then faults): --wl_in 1 --wl_out_local 1 --wl_out_remote 1
+    app_config.wl_alloc_factor_in = std::stod(o["wl_in"]);
+    app_config.wl_alloc_factor_out_local = std::stod(o["wl_out_local"]);
+    app_config.wl_alloc_factor_out_remote = std::stod(o["wl_out_remote"]);
     const std::string& a = o["application"];
     const bool directed = o["directed"] == "1";
     using grape::LoadStrategy;

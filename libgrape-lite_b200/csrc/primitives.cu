@@ -144,15 +144,13 @@ int scan_queue(const gl_frag* f, cudaStream_t s, const uint32_t* q, uint32_t n,
       case GL_LB_CM:
       case GL_LB_CMOLD:
       case GL_LB_CTA: {
-        // cm keeps every row inside its CTA tile; cta cuts long rows into
-        // grid-wide work items (k_hub_scan)
-        uint32_t hub_deg = lb == GL_LB_CTA ? kHubDeg : 0xFFFFFFFFu;
+        // CTA tiles; rows longer than hub_deg are cut into grid-wide 1024-entry work items (cta: 1024,
+        // cm: 8192 -- a row that long would serialise one CTA: measured 2x slower than the reference's cm)
+        uint32_t hub_deg = lb == GL_LB_CTA ? kHubDeg : 8 * kHubDeg;
         int g = std::min<int>(persistent_grid(k_queue_scan_cta<Op>, di->sm_count), (int) ((n + kTileV - 1) / kTileV));
         GL_LAUNCH(k_queue_scan_cta<Op>, g, kTB, s, ArraySrc{q}, n, er, op, ps.ctrl, ps.hubs, ps.hub_cap, hub_deg);
-        if (lb == GL_LB_CTA) {
-          int g2 = persistent_grid(k_hub_scan<Op>, di->sm_count);
-          GL_LAUNCH(k_hub_scan<Op>, g2, kTB, s, er, op, ps.ctrl, ps.hubs, ps.hub_cap);
-        }
+        int g2 = persistent_grid(k_hub_scan_tma<Op>, di->sm_count);
+        GL_LAUNCH(k_hub_scan_tma<Op>, g2, kTB, s, er, op, ps.ctrl, ps.hubs, ps.hub_cap);
         break;
       }
       case GL_LB_STRICT: {

@@ -73,7 +73,8 @@ def main():
     for app in a.apps.split(","):
         wmode = 1 if app == "sssp" else 0
         common = ["--application", app, "--rmat", "%d,16,1,%d" % (a.scale, wmode), "--lb", a.lbs, "--repeat", str(a.repeat),
-                  "--bfs_source", "maxdeg", "--sssp_source", "maxdeg", "--pr_mr", "10", "--pr_d", "0.85"]
+                  "--bfs_source", "maxdeg", "--sssp_source", "maxdeg", "--pr_mr", "10", "--pr_d", "0.85",
+                  "--wl_in", "1", "--wl_out_local", "1", "--wl_out_remote", "1"]
         for name, exe in (("reference-gpu", REF), ("b200-compat", OURS)):
             rows, err = run(exe, common)
             if rows is None:
