@@ -311,16 +311,22 @@ def sweep_apps(G, pkg, args, flush, frag_bfs, comm_bfs, scale_bfs, res_bfs):
         r3, a3, pr = measure_app(G, pkg, frag_u, comm_u, "pagerank", dict(cfgp, pr_pull=0), steps, warmup, flush,
                                  lambda _: m_in * 10, e2e=False)
         a3.close()
-        ap = pkg.App("pagerank", frag_u, comm_u, **dict(cfgp, pr_pull=1))
-        ap.query()
-        pull = ap.result()
+        # the deterministic pull formulation (single fragment: f32 contributions, hub values in shared memory)
+        cfg_pull = dict(cfgp, pr_pull=1)
+        if world == 1:
+            cfg_pull["reserved"] = {5: 1}
+        rp_, ap, pull = measure_app(G, pkg, frag_u, comm_u, "pagerank", cfg_pull, 2, 1, flush, lambda _: m_in * 10, e2e=False)
         ap.close()
         tot = G.reduce([float(pr.sum())])[0]
         err = G.reduce([float(np.max(np.abs(pr - pull) / pull))], "max")[0]
         r3 = clean(r3)
         rounds = [x for x in r3["ms_per_superstep"] if x > 0.05]
+        prounds = [x for x in rp_["ms_per_superstep"] if x > 0.05]
         r3.update(config="C3 PageRank 10 rounds d=0.85 push IncEval (f64 atomics), " + tag,
                   ms_per_round=float(np.median(rounds)) if rounds else None,
+                  pull_variant=dict(what="pull sweep, f32 contributions, f64 sums" + (", hub values in shared memory (k_pr_pull_hub)" if world == 1 else ""),
+                                    ms_per_query=rp_["ms_per_query"], ms_per_round=float(np.median(prounds)) if prounds else None,
+                                    frac_whole_query=rp_["frac_whole_query"]),
                   parity="sum(rank) = %.12f; max rel |push - pull| = %.2e (bar 1e-6)" % (tot, err),
                   parity_ok=bool(abs(tot - 1.0) < 1e-9 and err < 1e-6))
         apps["pagerank"] = r3
