@@ -101,8 +101,21 @@ typedef struct {
   int64_t oid_base;
 } gl_frag_desc;
 
-/* replaces HostFragment::__allocate_device_fragment__ (host_fragment.h:322-438) */
+/* replaces HostFragment::__allocate_device_fragment__ (host_fragment.h:322-438).
+ * Preconditions the library relies on (the reference's loaders satisfy them):
+ *  - rows sorted by neighbour lid, inner neighbours first; ovgid ascending;
+ *  - a DIRECTED fragment passes its in-edges in d->ie (without them BFS only pushes, PageRank pull
+ *    falls back to push and WCC / wcc_opt are refused);
+ *  - lids were assigned in ascending oid order inside each fragment and fids in ascending oid
+ *    blocks IF the smallest-label tie-breaks of CDLP / WCC must equal the reference's smallest-OID
+ *    rule (the apps tie-break on the smallest GID); with another vertex map attach a gl_vm_t
+ *    (gl_app_set_vertex_map) to get oids back and expect ties to follow gid order. */
 int gl_frag_create(gl_frag_t** out, const gl_frag_desc* d);
+/* HostFragment::PrepareToRunApp (host_fragment.h:122-215): split positions, outer ranges, the
+ * reverse adjacency of the outer copies and the destination-fragment information are part of the
+ * device layout from gl_frag_create on, so this only validates the request: need_mirror_info needs a
+ * communicator with a mirror area at sync time, need_build_device_vm is served by gl_vm_create. */
+int gl_frag_prepare(gl_frag_t*, int message_strategy, int need_split_edges, int need_mirror_info);
 
 /* Edge-list front end: replaces LoadGraph -> EVFragmentLoader ->
  * ImmutableEdgecutFragment::Init -> buildCSR -> upload
@@ -483,6 +496,21 @@ int gl_bitmap_create(uint32_t** out, uint64_t nbits);               /* zeroed */
 int gl_bitmap_clear(void* stream, uint32_t* bitmap, uint64_t nbits);  /* Clear(stream) */
 int gl_bitmap_count(void* stream, const uint32_t* bitmap, uint64_t nbits, uint64_t* count_host); /* Count(stream): syncs */
 int gl_bitmap_destroy(uint32_t* bitmap);
+
+/* Queue<T> (grape/cuda/utils/queue.h:30-140): a device array of vertex ids + its length on the device. */
+typedef struct gl_queue gl_queue_t;
+int gl_queue_create(gl_queue_t** out, uint32_t capacity);
+int gl_queue_clear(gl_queue_t*, void* stream);                          /* Clear(stream)            */
+int gl_queue_size(gl_queue_t*, void* stream, uint32_t* size_host);      /* size(stream): syncs      */
+int gl_queue_data(gl_queue_t*, uint32_t** data_dev, uint32_t** count_dev);  /* DeviceObject()       */
+/* bitmap -> queue without the host round trip of gl_compact_bitmap (count stays on the device) */
+int gl_queue_fill_from_bitmap(gl_queue_t*, void* stream, const uint32_t* bitmap, uint32_t n_bits);
+void gl_queue_destroy(gl_queue_t*);
+/* VertexArray<T> (grape/cuda/utils/vertex_array.h:34-169): device array + H2D / D2H */
+int gl_varray_create(void** out, uint64_t count, int elem_bytes, int fill_byte);
+int gl_varray_h2d(void* varray, const void* host, uint64_t count, int elem_bytes);
+int gl_varray_d2h(const void* varray, void* host, uint64_t count, int elem_bytes);
+int gl_varray_destroy(void* varray);
 
 /* device scratch helpers so a C/ctypes caller can run the primitives */
 int gl_dev_alloc(void** out, size_t bytes);

@@ -88,7 +88,9 @@ SYMBOLS = [
     "gl_mm_start_round", "gl_mm_finish_round", "gl_mm_to_terminate", "gl_mm_force_continue", "gl_mm_view_get",
     "gl_mm_bytes_sent", "gl_mm_destroy", "gl_mm_process", "gl_mm_send_outer", "gl_mm_mirror_plan", "gl_mm_sync_values_to_ghosts", "gl_mm_sync_bits_to_ghosts",
     "gl_allreduce", "gl_bitmap_create",
-    "gl_bitmap_clear", "gl_bitmap_count", "gl_bitmap_destroy", "gl_app_config_default", "gl_app_create", "gl_app_query", "gl_app_result",
+    "gl_bitmap_clear", "gl_bitmap_count", "gl_bitmap_destroy", "gl_frag_prepare", "gl_queue_create", "gl_queue_clear",
+    "gl_queue_size", "gl_queue_data", "gl_queue_fill_from_bitmap", "gl_queue_destroy", "gl_varray_create",
+    "gl_varray_h2d", "gl_varray_d2h", "gl_varray_destroy", "gl_app_config_default", "gl_app_create", "gl_app_query", "gl_app_result",
     "gl_app_result_oids", "gl_app_destroy", "gl_edge_scan_queue", "gl_compact_bitmap", "gl_dev_alloc",
     "gl_dev_free", "gl_dev_memset", "gl_dev_h2d", "gl_dev_d2h", "gl_dev_sync", "gl_kernel_launch_count",
     "gl_host_alloc_pinned", "gl_host_free_pinned",
@@ -112,6 +114,7 @@ def lib():
         L.gl_mm_bytes_sent.restype = C.c_uint64
         L.gl_mm_destroy.restype = None
         L.gl_vm_destroy.restype = None
+        L.gl_queue_destroy.restype = None
         for f in ("gl_frag_destroy", "gl_comm_destroy", "gl_app_destroy", "gl_app_config_default"):
             getattr(L, f).restype = None
         _LIB = L

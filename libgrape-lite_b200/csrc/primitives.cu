@@ -255,3 +255,108 @@ int gl_compact_bitmap(void* stream, const uint32_t* bitmap, uint32_t n_bits,
 }
 
 }  // extern "C"
+
+// ---- Face-2 containers (Queue / VertexArray) and PrepareToRunApp -------------------------------
+struct gl_queue {
+  uint32_t* data = nullptr;
+  uint32_t* count = nullptr;
+  uint32_t capacity = 0;
+};
+
+extern "C" {
+
+int gl_queue_create(gl_queue_t** out, uint32_t capacity) {
+  GL_ARG(out, "null argument");
+  DeviceInfo* di;
+  GL_TRY(device_info(&di));
+  gl_queue* q = new gl_queue;
+  q->capacity = capacity;
+  if (cudaMalloc(&q->data, sizeof(uint32_t) * std::max<uint32_t>(capacity, 1)) != cudaSuccess ||
+      cudaMalloc(&q->count, sizeof(uint32_t)) != cudaSuccess || cudaMemset(q->count, 0, 4) != cudaSuccess) {
+    gl_queue_destroy(q);
+    set_error("gl_queue_create: device allocation failed");
+    return GL_ERR_NOMEM;
+  }
+  *out = q;
+  return GL_OK;
+}
+int gl_queue_clear(gl_queue_t* q, void* stream) {
+  GL_ARG(q, "null argument");
+  GL_CUDA(cudaMemsetAsync(q->count, 0, 4, (cudaStream_t) stream));
+  return GL_OK;
+}
+int gl_queue_size(gl_queue_t* q, void* stream, uint32_t* size_host) {
+  GL_ARG(q && size_host, "null argument");
+  GL_CUDA(cudaMemcpyAsync(size_host, q->count, 4, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+  GL_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+  if (*size_host > q->capacity) *size_host = q->capacity;
+  return GL_OK;
+}
+int gl_queue_data(gl_queue_t* q, uint32_t** data_dev, uint32_t** count_dev) {
+  GL_ARG(q, "null argument");
+  if (data_dev) *data_dev = q->data;
+  if (count_dev) *count_dev = q->count;
+  return GL_OK;
+}
+int gl_queue_fill_from_bitmap(gl_queue_t* q, void* stream, const uint32_t* bitmap, uint32_t n_bits) {
+  GL_ARG(q && bitmap, "null argument");
+  GL_ARG(n_bits <= q->capacity, "gl_queue_fill_from_bitmap: the queue is smaller than the bitmap");
+  cudaStream_t s = (cudaStream_t) stream;
+  DeviceInfo* di;
+  GL_TRY(device_info(&di));
+  GL_CUDA(cudaMemsetAsync(q->count, 0, 4, s));
+  if (n_bits) {
+    int g = std::max(1, std::min<int>(di->sm_count * 8, (int) ((n_bits + kTB - 1) / kTB)));
+    k_compact<<<g, kTB, 0, s>>>(bitmap, n_bits, q->data, q->count);
+    GL_COUNT_LAUNCH();
+    GL_CUDA(cudaGetLastError());
+  }
+  return GL_OK;
+}
+void gl_queue_destroy(gl_queue_t* q) {
+  if (!q) return;
+  cudaFree(q->data);
+  cudaFree(q->count);
+  delete q;
+}
+
+int gl_varray_create(void** out, uint64_t count, int elem_bytes, int fill_byte) {
+  GL_ARG(out && elem_bytes > 0, "bad argument");
+  DeviceInfo* di;
+  GL_TRY(device_info(&di));
+  const size_t bytes = std::max<size_t>((size_t) count * (size_t) elem_bytes, 16);
+  GL_CUDA(cudaMalloc(out, bytes));
+  GL_CUDA(cudaMemset(*out, fill_byte, bytes));
+  return GL_OK;
+}
+int gl_varray_h2d(void* v, const void* host, uint64_t count, int elem_bytes) {
+  GL_ARG(v && host, "null argument");
+  GL_CUDA(cudaMemcpy(v, host, (size_t) count * (size_t) elem_bytes, cudaMemcpyHostToDevice));
+  return GL_OK;
+}
+int gl_varray_d2h(const void* v, void* host, uint64_t count, int elem_bytes) {
+  GL_ARG(v && host, "null argument");
+  GL_CUDA(cudaMemcpy(host, v, (size_t) count * (size_t) elem_bytes, cudaMemcpyDeviceToHost));
+  return GL_OK;
+}
+int gl_varray_destroy(void* v) {
+  if (v) GL_CUDA(cudaFree(v));
+  return GL_OK;
+}
+
+int gl_frag_prepare(gl_frag_t* f, int message_strategy, int need_split_edges, int need_mirror_info) {
+  GL_ARG(f, "null argument");
+  GL_ARG(message_strategy >= 0 && message_strategy <= 3, "gl_frag_prepare: unknown message strategy");
+  if (f->offloaded) {
+    set_error("fragment topology is offloaded");
+    return GL_ERR_STATE;
+  }
+  if (need_split_edges && (!f->oe.split || (f->directed && !f->ie_alias_oe && !f->ie.split))) {
+    set_error("gl_frag_prepare: split positions are missing");
+    return GL_ERR_STATE;
+  }
+  (void) need_mirror_info;   // mirror lists are exchanged by gl_mm_mirror_plan (needs the communicator)
+  return GL_OK;
+}
+
+}  // extern "C"

@@ -109,3 +109,55 @@ def test_empty_queue_and_empty_bitmap(graph):
     d_bm.fill(0)
     d_out = P.DeviceArray(nbytes=4 * n)
     assert P.compact_bitmap(d_bm, n, d_out) == 0
+
+
+def test_face2_containers_queue_varray_prepare():
+    """gl_queue_* (Queue), gl_varray_* (VertexArray), gl_bitmap_* (DenseVertexSet), gl_frag_prepare."""
+    import ctypes as C
+    P = pkg()
+    L = P.lib()
+    n = 100000
+    rng = np.random.default_rng(5)
+    bits = rng.random(n) < 0.07
+    words = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+    idx = np.nonzero(bits)[0]
+    np.bitwise_or.at(words, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+    bm = C.POINTER(C.c_uint32)()
+    P.check(L.gl_bitmap_create(C.byref(bm), C.c_uint64(n)))
+    P.check(L.gl_dev_h2d(bm, words.ctypes.data_as(C.c_void_p), C.c_size_t(words.nbytes)))
+    cnt = C.c_uint64()
+    P.check(L.gl_bitmap_count(None, bm, C.c_uint64(n), C.byref(cnt)))
+    assert cnt.value == len(idx)
+    q = C.c_void_p()
+    P.check(L.gl_queue_create(C.byref(q), C.c_uint32(n)))
+    P.check(L.gl_queue_fill_from_bitmap(q, None, bm, C.c_uint32(n)))
+    size = C.c_uint32()
+    P.check(L.gl_queue_size(q, None, C.byref(size)))
+    assert size.value == len(idx)
+    data, dcount = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+    P.check(L.gl_queue_data(q, C.byref(data), C.byref(dcount)))
+    got = np.empty(size.value, dtype=np.uint32)
+    P.check(L.gl_dev_d2h(got.ctypes.data_as(C.c_void_p), data, C.c_size_t(got.nbytes)))
+    assert np.array_equal(np.sort(got), idx.astype(np.uint32))
+    P.check(L.gl_queue_clear(q, None))
+    P.check(L.gl_queue_size(q, None, C.byref(size)))
+    assert size.value == 0
+    L.gl_queue_destroy(q)
+    P.check(L.gl_bitmap_clear(None, bm, C.c_uint64(n)))
+    P.check(L.gl_bitmap_count(None, bm, C.c_uint64(n), C.byref(cnt)))
+    assert cnt.value == 0
+    P.check(L.gl_bitmap_destroy(bm))
+    va = C.c_void_p()
+    vals = rng.random(1000)
+    P.check(L.gl_varray_create(C.byref(va), C.c_uint64(1000), 8, 0))
+    P.check(L.gl_varray_h2d(va, vals.ctypes.data_as(C.c_void_p), C.c_uint64(1000), 8))
+    back = np.empty(1000)
+    P.check(L.gl_varray_d2h(va, back.ctypes.data_as(C.c_void_p), C.c_uint64(1000), 8))
+    assert np.array_equal(back, vals)
+    P.check(L.gl_varray_destroy(va))
+    frag = P.Fragment.rmat(8, 16, seed=3)
+    P.check(L.gl_frag_prepare(frag.h, 0, 1, 0))
+    frag.offload()
+    assert L.gl_frag_prepare(frag.h, 0, 1, 0) != 0
+    frag.reload()
+    frag.close()
