@@ -414,6 +414,9 @@ typedef struct {
                             [3] >=4: number of BFS level bitmaps (forces spills)
                             [4] 1: PageRank f32 pull without the shared-memory hub table (A/B)
                             [5] 1: PageRank pull gathers f32 contributions
+                            [7] 1: fused multi-fragment BFS ships per-holder bit-compressed
+                                   frontier slices (round-1 scheme) instead of replicating
+                                   the global frontier bitmap
                             [6] 1: BFS result as an int64 device array + one D2H
                                    (default: u8 depths over PCIe, widened on the host) */
 } gl_app_config;

@@ -79,6 +79,22 @@ __global__ void k_bfs_popc(const uint32_t* bm, uint32_t words, unsigned long lon
   if (lane_id() == 0 && c) atomicAdd(out, c);
 }
 
+// lid -> gid of every CSR entry / of the hub-neighbour table (global-frontier pull, several fragments)
+__global__ void k_bfs_gcol(const uint32_t* __restrict__ col, uint64_t m, uint32_t ivnum, uint32_t my_gid0,
+                           const uint32_t* __restrict__ ovgid, uint32_t* gcol) {
+  for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t) gridDim.x * blockDim.x) {
+    const uint32_t c = col[i];
+    gcol[i] = c < ivnum ? (my_gid0 | c) : ovgid[c - ivnum];
+  }
+}
+__global__ void k_bfs_gid_table(const uint32_t* __restrict__ lids, uint32_t n, uint32_t ivnum, uint32_t my_gid0,
+                                const uint32_t* __restrict__ ovgid, uint32_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = lids[i];
+  out[i] = c == kInfU32 ? kInfU32 : (c < ivnum ? (my_gid0 | c) : ovgid[c - ivnum]);
+}
+
 __global__ void k_bfs_seed(uint32_t src, uint32_t* lv0, uint32_t* vis) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     lv0[src >> 5] |= 1u << (src & 31);
@@ -137,7 +153,24 @@ struct PullArgs {
   const uint32_t* hub_nbr;
   uint32_t ivnum;
   const uint32_t* nz;
+  // Several fragments, fused kernel: `col` / `hub_nbr` hold GIDs and the frontier is the
+  // REPLICATED GLOBAL bitmap, kept as one segment per owner fragment (seg[f] = the bits of
+  // fragment f's inner vertices; the owners store them into every peer over NVLink).  null:
+  // `col` holds lids and the frontier is the local bitmap passed to the phase.
+  const uint32_t* const* seg;
+  int fid_offset;
+  uint32_t id_mask;
+  uint32_t hub_dummy;   // a valid id for the branch-free probes of non-candidates (lid 0 / my gid 0)
 };
+
+// is vertex `id` in the frontier?  (segments are written by peers: L1 is bypassed)
+GL_DEV bool front_test(const PullArgs& a, const uint32_t* cur, uint32_t id) {
+  if (a.seg) {
+    const uint32_t f = id >> a.fid_offset, l = id & a.id_mask;
+    return (__ldcg(a.seg[f] + (l >> 5)) >> (l & 31)) & 1u;
+  }
+  return (cur[id >> 5] >> (id & 31)) & 1u;
+}
 
 // One super-tile = 8192 vertices = 256 words; thread t owns word t: it probes
 // the hub neighbour of each of its (up to 32) candidates with eight
@@ -175,15 +208,15 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
         const bool c1 = (nib & 2u) && h.y != kInfU32;
         const bool c2 = (nib & 4u) && h.z != kInfU32;
         const bool c3 = (nib & 8u) && h.w != kInfU32;
-        const uint32_t i0 = c0 ? h.x : 0u, i1 = c1 ? h.y : 0u;
-        const uint32_t i2 = c2 ? h.z : 0u, i3 = c3 ? h.w : 0u;
-        const uint32_t w0 = cur[i0 >> 5], w1 = cur[i1 >> 5];
-        const uint32_t w2 = cur[i2 >> 5], w3 = cur[i3 >> 5];
+        const uint32_t i0 = c0 ? h.x : a.hub_dummy, i1 = c1 ? h.y : a.hub_dummy;
+        const uint32_t i2 = c2 ? h.z : a.hub_dummy, i3 = c3 ? h.w : a.hub_dummy;
+        const bool t0 = front_test(a, cur, i0), t1 = front_test(a, cur, i1);
+        const bool t2 = front_test(a, cur, i2), t3 = front_test(a, cur, i3);
         uint32_t r = 0;
-        r |= (c0 && ((w0 >> (i0 & 31)) & 1u)) ? 1u : 0u;
-        r |= (c1 && ((w1 >> (i1 & 31)) & 1u)) ? 2u : 0u;
-        r |= (c2 && ((w2 >> (i2 & 31)) & 1u)) ? 4u : 0u;
-        r |= (c3 && ((w3 >> (i3 & 31)) & 1u)) ? 8u : 0u;
+        r |= (c0 && t0) ? 1u : 0u;
+        r |= (c1 && t1) ? 2u : 0u;
+        r |= (c2 && t2) ? 4u : 0u;
+        r |= (c3 && t3) ? 8u : 0u;
         res |= r << (4 * j);
       }
       scanned += __popc(word);
@@ -216,7 +249,7 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
         bool found = false;
         uint32_t p = 0;
         for (; p < lim; ++p) {
-          if (bit_test(cur, row[p])) {
+          if (front_test(a, cur, row[p])) {
             found = true;
             ++p;
             break;
@@ -238,7 +271,7 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
         uint32_t p = kPullSerialCap;
         for (; p < len; p += 32) {
           const uint32_t q = p + lane_id();
-          const bool h = q < len && bit_test(cur, row[q]);
+          const bool h = q < len && front_test(a, cur, row[q]);
           if (__any_sync(0xffffffffu, h)) {
             hit = true;
             p += 32;
@@ -540,6 +573,10 @@ struct XComm {
   char* const* msend[2];
   const char* const* mrecv[2];
   const uint32_t* ghost_range;
+  // replicated global frontier (pull levels): the mirror slots of one parity, seen as one
+  // bitmap segment per owner fragment; seg_words = words of the largest fragment's segment
+  int global_front;
+  uint32_t seg_words, my_words;
 };
 
 struct XSmem {
@@ -696,6 +733,35 @@ GL_DEV void mirror_unpack(const XComm& x, uint32_t par, uint32_t* bitmap) {
     }
   }
 }
+// Owner -> everybody: store the non-zero words of my frontier segment into the (parity, me)
+// mirror slot of every fragment, my own included (the slots are kept zero between uses).
+GL_DEV bool front_ship(const XComm& x, uint32_t par, const uint32_t* bitmap) {
+  const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+  const uint64_t gtid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  bool wrote = false;
+  for (uint64_t w = gtid; w < x.my_words; w += nthreads) {
+    const uint32_t v = bitmap[w];
+    if (!v) continue;
+    for (uint32_t p = 0; p < x.fnum; ++p) {
+      uint32_t* dst = p == x.fid ? (uint32_t*) x.mrecv[par][p] : (uint32_t*) x.msend[par][p];
+      dst[w] = v;
+    }
+    wrote = x.fnum > 1;
+  }
+  return wrote;
+}
+// the segments of parity `par` were consumed: back to zero for their next use (two shipments later)
+GL_DEV void front_zero(const XComm& x, uint32_t par) {
+  const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+  const uint64_t gtid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t total = (uint64_t) x.fnum * x.seg_words;
+  for (uint64_t i = gtid; i < total; i += nthreads) {
+    const uint32_t f = (uint32_t) (i / x.seg_words), w = (uint32_t) (i % x.seg_words);
+    uint32_t* seg = (uint32_t*) x.mrecv[par][f];
+    if (__ldcg(seg + w)) seg[w] = 0u;
+  }
+}
+
 GL_DEV bool mirror_sync_bits(cg::grid_group& grid, const XComm& x, XSmem& xs, unsigned long long tag,
                              uint32_t par, uint32_t* bitmap, BfsFusedCtl* ctl) {
   const bool wrote = mirror_pack(x, par, bitmap);
@@ -776,10 +842,16 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
 #define GL_MARK(k) do { if (gtid == 0 && tl < 32) ctl->ph[tl][k] = global_ns(); } while (0)
     GL_MARK(0);
     if (nphase != 1) {
+      if (premirrored && x.global_front) {
+        front_zero(x, mseq & 1);   // the speculative shipment of this frontier stays unused
+        grid.sync();
+      }
       premirrored = false;   // (a speculative shipment of this frontier stays unused)
-      if (phase == 1) {
+      if (phase == 1 && !x.global_front) {
         // leaving the pull phase: outer copies learn which vertices their
         // owners visited meanwhile, so they are not reported again
+        // (global-frontier scheme: skipped -- a holder may report an already visited vertex once
+        //  more, the owner's visited test drops it; the tail frontiers are tiny)
         ++mseq;
         if (!mirror_sync_bits(grid, x, sm.xs, tag++, mseq & 1, a.vis, ctl)) return;
       }
@@ -829,6 +901,28 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
       GL_MARK(5);
       ++msg_round;
     } else {
+      if (x.global_front) {
+        if (!premirrored) {
+          // the frontier came out of a push level: replicate my segment of it now
+          ++mseq;
+          const bool wrote0 = front_ship(x, mseq & 1, cur);
+          long long dummy[3];
+          if (!xsync(grid, x, sm.xs, tag++, -1, nullptr, 0, 0, ctl, dummy, wrote0)) return;
+        }
+        GL_MARK(1);
+        PullArgs pa = a.pa;
+        pa.seg = (const uint32_t* const*) x.mrecv[mseq & 1];   // every owner's segment of this level's frontier
+        bfs_pull_phase(sm.pull, pa, cur, a.vis, nxt, C, acc);
+        flush_acc(acc, C);
+        grid.sync();
+        GL_MARK(2);
+        front_zero(x, mseq & 1);            // consumed; this parity is written again two shipments from now
+        ++mseq;
+        const bool wrote = front_ship(x, mseq & 1, nxt);   // next level's frontier rides with the statistics
+        if (!xsync(grid, x, sm.xs, tag++, -1, C, 0, 0, ctl, S, wrote)) return;
+        premirrored = true;
+        GL_MARK(4);
+      } else {
       if (!premirrored) {
         ++mseq;
         if (!mirror_sync_bits(grid, x, sm.xs, tag++, mseq & 1, cur, ctl)) return;
@@ -850,6 +944,7 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
       if (!xsync(grid, x, sm.xs, tag++, -1, C, 0, 0, ctl, S, wrote)) return;
       premirrored = true;
       GL_MARK(4);
+      }
     }
 #undef GL_MARK
     phase = nphase;
@@ -948,6 +1043,10 @@ struct BfsApp : gl_app {
   const uint64_t* p_rp = nullptr;
   const uint32_t* p_col = nullptr;
   uint32_t* nz_in = nullptr;   // directed: inner vertices with in-degree > 0
+  // several fragments, fused kernel: gid-space copies for the replicated global frontier
+  uint32_t *gcol = nullptr, *hub_nbr_g = nullptr;
+  uint32_t seg_words = 0;
+  bool global_front = false;
   uint32_t *perm = nullptr, *order = nullptr, *nz_p = nullptr, *col_p = nullptr;
   uint64_t* rp_p = nullptr;
   uint32_t src_ = 0;
@@ -981,6 +1080,8 @@ struct BfsApp : gl_app {
     cudaFree(col_p);
     cudaFree(rp_p);
     cudaFree(nz_in);
+    cudaFree(gcol);
+    cudaFree(hub_nbr_g);
     cudaFree(d_out8);
     if (h_out8) cudaFreeHost(h_out8);
     for (auto e : ev8)
@@ -1071,6 +1172,23 @@ struct BfsApp : gl_app {
       long long lo = (long long) max_lv, dummy = 0;
       GL_TRY(mm.PeerAllReduce(eng.stream, &lo, &dummy, &c, 1));
       max_lv = (uint32_t) lo;
+      // Replicated global frontier for the pull levels of the fused kernel (cfg.reserved[7] = 1: the
+      // round-1 scheme, per-holder bit-compressed shipments): gid copies of the pull adjacency and of
+      // the hub-neighbour table; the mirror slots of one parity hold one frontier segment per owner.
+      long long mw = (long long) bm_words(fv.ivnum), unused = 0;
+      GL_TRY(mm.PeerAllReduce(eng.stream, &mw, &unused, &c, 2));
+      seg_words = (uint32_t) mw;
+      global_front = can_pull() && cfg.reserved[7] == 0 && (size_t) seg_words * 4 <= comm->mirror_bytes;
+      if (global_front) {
+        const uint64_t m = (fv.directed ? frag->ie.entries : frag->oe.entries);
+        const uint32_t gid0 = fv.fid << fv.fid_offset;
+        GL_CUDA(cudaMalloc(&gcol, sizeof(uint32_t) * (m + 16)));
+        GL_CUDA(cudaMalloc(&hub_nbr_g, sizeof(uint32_t) * ((size_t) fv.ivnum + kSuperV)));
+        GL_CUDA(cudaMemsetAsync(hub_nbr_g, 0xFF, sizeof(uint32_t) * ((size_t) fv.ivnum + kSuperV), eng.stream));
+        if (m) GL_LAUNCH(k_bfs_gcol, eng.sm_count * 8, 256, eng.stream, p_col, m, fv.ivnum, gid0, fv.ovgid, gcol);
+        if (fv.ivnum) GL_LAUNCH(k_bfs_gid_table, (fv.ivnum + 255) / 256, 256, eng.stream, hub_nbr, fv.ivnum, fv.ivnum, gid0, fv.ovgid, hub_nbr_g);
+        GL_CUDA(cudaStreamSynchronize(eng.stream));
+      }
     }
     return GL_OK;
   }
@@ -1084,6 +1202,18 @@ struct BfsApp : gl_app {
     depth_base = 0;
     GL_CUDA(cudaMemsetAsync(vis, 0, sizeof(uint32_t) * words, s));
     GL_CUDA(cudaMemsetAsync(remote, 0, sizeof(uint32_t) * words, s));
+    if (global_front && comm->mirror_dirty) {
+      // the frontier segments (the first seg_words words of every mirror slot) must be zero when the
+      // query starts; the fused kernel leaves them zero, other users of the mirror area do not.
+      // Collective by construction: every rank sees the same history of mirror-area users.
+      GL_TRY(mm.PeerBarrier(s));
+      for (int par = 0; par < 2; ++par)
+        for (uint32_t f = 0; f < fv.fnum; ++f)
+          GL_CUDA(cudaMemsetAsync(comm->local_base + comm->mirror_off(par, f), 0, (size_t) seg_words * 4, s));
+      GL_CUDA(cudaStreamSynchronize(s));
+      GL_TRY(mm.PeerBarrier(s));
+      comm->mirror_dirty = false;
+    }
     curr_depth = 0;
     used_lv = 0;
     n_f = m_f = visited_edges = 0;
@@ -1117,7 +1247,7 @@ struct BfsApp : gl_app {
   }
 
   PullArgs pull_args() const {
-    return PullArgs{p_rp, row_end(), p_col, hub_nbr, fv.ivnum, g_nz};
+    return PullArgs{p_rp, row_end(), p_col, hub_nbr, fv.ivnum, g_nz, nullptr, 0, 0, 0};
   }
 
   bool fused() const {
@@ -1174,6 +1304,16 @@ struct BfsApp : gl_app {
       x.plan = mm.bits_plan();
       if (!mm.mirror_sorted) x.plan.mask = nullptr;
       x.ghost_range = mm.d_ghost_range;
+      x.global_front = global_front ? 1 : 0;
+      x.seg_words = seg_words;
+      x.my_words = (uint32_t) bm_words(fv.ivnum);
+      if (global_front) {
+        a.pa.col = gcol;
+        a.pa.hub_nbr = hub_nbr_g;
+        a.pa.fid_offset = fv.fid_offset;
+        a.pa.id_mask = fv.id_mask;
+        a.pa.hub_dummy = fv.fid << fv.fid_offset;
+      }
       for (int par = 0; par < 2; ++par) {
         x.slot_at_peer[par] = mm.d_peer_slot[par];
         x.send_slot[par] = mm.d_send_slot[par];

@@ -291,6 +291,7 @@ int MessageManager::BuildMirrorPlan(cudaStream_t s, const gl_frag_view& fv) {
   plan_built = true;
   plan_ivnum = fv.ivnum;
   if (fnum == 1) return GL_OK;
+  comm->mirror_dirty = true;
   if (comm->mirror_bytes == 0) {
     set_error("communicator was created without a mirror-sync area (mirror_bytes = 0)");
     return GL_ERR_COMM;
@@ -393,6 +394,7 @@ MirrorBitsPlan MessageManager::bits_plan() const {
 
 int MessageManager::SyncBitsToGhosts(cudaStream_t s, uint32_t* bitmap) {
   if (fnum == 1) return GL_OK;
+  comm->mirror_dirty = true;
   const int par = (int) (++mirror_seq & 1);
   if (mirror_total && mirror_sorted) {
     GL_LAUNCH(k_mirror_pack_bits2, 148 * 8, 256, s, bits_plan(), bitmap, d_msend[par]);
@@ -410,6 +412,7 @@ int MessageManager::SyncBitsToGhosts(cudaStream_t s, uint32_t* bitmap) {
 
 int MessageManager::SyncValuesToGhosts(cudaStream_t s, void* values, int elem_bytes) {
   if (fnum == 1) return GL_OK;
+  comm->mirror_dirty = true;
   const int par = (int) (++mirror_seq & 1);
   dim3 grid(148 * 8, fnum);
   if (mirror_total) {
@@ -751,6 +754,7 @@ extern "C" int gl_comm_peer_write_us(gl_comm_t* c, size_t bytes, int vec16, int 
     set_error("gl_comm_peer_write_us needs an opened communicator with fnum >= 2");
     return GL_ERR_STATE;
   }
+  c->mirror_dirty = true;
   bytes &= ~(size_t) 15;
   if (bytes == 0 || bytes > c->mirror_bytes) {
     set_error("gl_comm_peer_write_us: bytes must be in (0, mirror_bytes]");

@@ -40,6 +40,9 @@ struct gl_comm {
   std::vector<char*> peer_base;  // [fnum]; peer_base[fid] == local_base
   bool opened = false;
   unsigned long long seq_base = 0;  // last collective sequence number used on this communicator
+  // something other than the fused BFS's frontier segments was written into the mirror slots
+  // (value / bit syncs, mirror-plan requests): that app re-zeroes its segments before a query
+  bool mirror_dirty = true;
   size_t total_bytes() const {
     return GL_COMM_HEADER + 2 * (size_t) fnum * (landing_bytes + mirror_bytes);
   }

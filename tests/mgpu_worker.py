@@ -82,7 +82,7 @@ def main():
         mm.close()
         return out, rounds, total
 
-    for wmode, apps in ((0, ["bfs", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "wcc_opt", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp", "face2_sssp"])):
+    for wmode, apps in ((0, ["bfs", "bfs_r1ship", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "wcc_opt", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp", "face2_sssp"])):
         n = 1 << scale
         frag = pkg.Fragment.rmat(scale, 16, seed=17, weight_mode=wmode, fid=rank, fnum=world)
         comm = gdist.make_comm(rank, world, frag.ivnum)
@@ -108,6 +108,8 @@ def main():
                 # *_step = one superstep per round through the host loop
                 cfg = dict(source_oid=source, direction_opt=0 if "push" in name else 1,
                            fuse_supersteps=0 if name.endswith("_step") else 1)
+                if name == "bfs_r1ship":     # round-1 frontier shipment (per-holder bit-compressed slices)
+                    cfg["reserved"] = {7: 1}
             elif name == "sssp":
                 cfg = dict(source_oid=source)
             elif name.startswith("pagerank"):

@@ -49,4 +49,4 @@ def test_multi_fragment_one_device(nproc, scale):
     p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     sys.stdout.write(p.stdout[-4000:])
     assert p.returncode == 0, p.stdout[-4000:]
-    assert p.stdout.count(" OK") >= 15, p.stdout[-4000:]
+    assert p.stdout.count(" OK") >= 16, p.stdout[-4000:]
