@@ -66,6 +66,11 @@ struct gl_app {
   virtual size_t ResultElemBytes() const = 0;
   virtual void FillStats(gl_query_stats*) {}   // apps that time supersteps on the device
   virtual void AfterRound() {}                 // runs after every FinishARound (global round statistics)
+  // Apps whose whole query is one launch record this event in-stream right after the query's last
+  // device operation (kernel + control-block read-back); query_ms then ends there instead of at the
+  // event the host records after it woke up from the stream synchronisation (host latency is part of
+  // e2e, not of the device-timed value).  null: the worker loop's last event.
+  cudaEvent_t query_end = nullptr;
   // record per-superstep stats (called by apps after fetch_ctrl)
   void note_step(uint64_t entries, uint32_t frontier, int mode) {
     rec.entries.push_back(entries);

@@ -49,7 +49,17 @@ struct OpBfsPush {
   uint32_t* remote;
   const uint64_t* rp;
   uint32_t ivnum;
+  // Frontier-edge statistic for the push -> pull switch (only read while the query is still in its
+  // first push phase).  deg8 != null: one byte per vertex (1 + floor(log2(degree)), L2-resident 16 MB at
+  // 2^24 vertices) instead of a random 16-byte row-pointer read per discovered vertex (134 MB array);
+  // the estimate 1.5 * 2^(k-1) is within +-33 %, the switch thresholds are an order-of-magnitude rule.
+  const uint8_t* deg8 = nullptr;
   GL_DEV Meta assign(uint32_t) const { return 0; }
+  GL_DEV unsigned long long degree_of(uint32_t v) const {
+    if (!deg8) return rp[v + 1] - rp[v];
+    const uint32_t k = deg8[v];
+    return k == 0 ? 0ull : (k == 1 ? 1ull : (3ull << (k - 2)));
+  }
   GL_DEV void edge(uint32_t, Meta, uint32_t v, W, ScanAcc& acc) const {
     if (bit_test(vis, v)) return;        // plain (possibly stale) read first
     if (!bit_set_atomic(vis, v)) return; // somebody else won
@@ -57,13 +67,20 @@ struct OpBfsPush {
     acc.touched++;
     if (v < ivnum) {
       acc.next_count++;
-      acc.next_edges += rp[v + 1] - rp[v];
+      acc.next_edges += degree_of(v);
     } else {
       bit_set_atomic(remote, v);
       acc.remote++;
     }
   }
 };
+
+__global__ void k_bfs_deg8(const uint64_t* rp, uint32_t n, uint8_t* deg8) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long d = rp[i + 1] - rp[i];
+  deg8[i] = d == 0 ? 0 : (uint8_t) (64 - __clzll((long long) d));   // 1 + floor(log2 d)
+}
 
 __global__ void k_bfs_nz(const uint64_t* rp, uint32_t n, uint32_t* nz) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +112,13 @@ __global__ void k_bfs_gid_table(const uint32_t* __restrict__ lids, uint32_t n, u
   out[i] = c == kInfU32 ? kInfU32 : (c < ivnum ? (my_gid0 | c) : ovgid[c - ivnum]);
 }
 
+__global__ void k_bfs_deg32(const uint64_t* __restrict__ rp, uint32_t ivnum, uint32_t tvnum, uint32_t* deg) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tvnum) return;
+  unsigned long long d = i < ivnum ? rp[i + 1] - rp[i] : 0;
+  deg[i] = d > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t) d;
+}
+
 __global__ void k_bfs_seed(uint32_t src, uint32_t* lv0, uint32_t* vis) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     lv0[src >> 5] |= 1u << (src & 31);
@@ -106,15 +130,17 @@ __global__ void k_bfs_seed(uint32_t src, uint32_t* lv0, uint32_t* vis) {
 // first in the row); one warp per row.  Built once per app.
 __global__ void __launch_bounds__(256)
 k_bfs_hub_nbr(const uint64_t* __restrict__ rp, const uint64_t* __restrict__ row_end,
-              const uint32_t* __restrict__ col, uint32_t ivnum, uint32_t* hub_nbr) {
+              const uint32_t* __restrict__ col, uint32_t ivnum, uint32_t* hub_nbr,
+              const uint32_t* __restrict__ deg_all = nullptr) {
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < ivnum; v += warps) {
     const uint64_t b = rp[v], e = row_end[v];
     unsigned long long best = 0;
     for (uint64_t p = b + lane_id(); p < e; p += 32) {
       uint32_t u = col[p];
-      // outer copies have no local row: rank them below every inner neighbour
-      unsigned long long dg = u < ivnum ? rp[u + 1] - rp[u] + 1 : 1;
+      // outer copies have no local row: their owner's degree when it was synced (deg_all), else they
+      // rank below every inner neighbour
+      unsigned long long dg = deg_all ? (unsigned long long) deg_all[u] + 1 : (u < ivnum ? rp[u + 1] - rp[u] + 1 : 1);
       if (dg > 0xFFFFFFFFull) dg = 0xFFFFFFFFull;
       uint64_t off = p - b;
       if (off > 0xFFFFFFFEull) off = 0xFFFFFFFEull;
@@ -161,13 +187,21 @@ struct PullArgs {
   int fid_offset;
   uint32_t id_mask;
   uint32_t hub_dummy;   // a valid id for the branch-free probes of non-candidates (lid 0 / my gid 0)
+  uint32_t seg_off;     // word offset of this level's generation inside every segment slot
+  int seg_cached;       // 1: these addresses were never read before in this launch -> L1 may cache them
 };
 
 // is vertex `id` in the frontier?  (segments are written by peers: L1 is bypassed)
 GL_DEV bool front_test(const PullArgs& a, const uint32_t* cur, uint32_t id) {
   if (a.seg) {
+    // A frontier bit is probed ~10^7 times per level: it must be an L1 hit.  L1 is not coherent
+    // with the peers' stores, so every pull level of a launch reads a FRESH generation of the
+    // segments (addresses no SM has loaded before in this launch); once the generations wrap
+    // around (seg_cached = 0) the probes bypass L1.
     const uint32_t f = id >> a.fid_offset, l = id & a.id_mask;
-    return (__ldcg(a.seg[f] + (l >> 5)) >> (l & 31)) & 1u;
+    const uint32_t* p = a.seg[f] + a.seg_off + (l >> 5);
+    const uint32_t w = a.seg_cached ? *p : __ldcg(p);
+    return (w >> (l & 31)) & 1u;
   }
   return (cur[id >> 5] >> (id & 31)) & 1u;
 }
@@ -452,6 +486,7 @@ struct BfsFusedArgs {
   HubItem* hubs;
   uint32_t hub_cap, hub_deg;
   int hub_tma;       // hub phase staged through the TMA engine (GL_HUB_TMA=0: plain loads)
+  const uint8_t* deg8;   // byte-sized degree classes for the frontier-edge statistic (OpBfsPush)
 };
 
 // Level d reads lv[d] and writes lv[d+1] (pre-zeroed).  Every thread derives
@@ -495,7 +530,7 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedAr
     uint32_t* nxt = a.lv + (size_t) (depth + 1) * a.words;
     ScanAcc acc;
     if (phase != 1) {
-      OpBfsPush op{a.vis, nxt, nullptr, a.er.rp, a.pa.ivnum};
+      OpBfsPush op{a.vis, nxt, nullptr, a.er.rp, a.pa.ivnum, a.deg8};
       frontier_scan_phase<OpBfsPush>(sm.scan, cur, a.pa.ivnum, a.er, op, C, a.hubs, a.hub_cap, a.hub_deg, acc);
       grid.sync();
       if (a.hub_tma) hub_scan_phase_tma<OpBfsPush>(sm.hub, a.er, op, C, a.hubs, a.hub_cap, acc);
@@ -577,6 +612,7 @@ struct XComm {
   // bitmap segment per owner fragment; seg_words = words of the largest fragment's segment
   int global_front;
   uint32_t seg_words, my_words;
+  uint32_t seg_stride, seg_gens;   // words between two generations inside a slot; generations per parity
 };
 
 struct XSmem {
@@ -735,7 +771,7 @@ GL_DEV void mirror_unpack(const XComm& x, uint32_t par, uint32_t* bitmap) {
 }
 // Owner -> everybody: store the non-zero words of my frontier segment into the (parity, me)
 // mirror slot of every fragment, my own included (the slots are kept zero between uses).
-GL_DEV bool front_ship(const XComm& x, uint32_t par, const uint32_t* bitmap) {
+GL_DEV bool front_ship(const XComm& x, uint32_t par, uint32_t off, const uint32_t* bitmap) {
   const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
   const uint64_t gtid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   bool wrote = false;
@@ -743,7 +779,7 @@ GL_DEV bool front_ship(const XComm& x, uint32_t par, const uint32_t* bitmap) {
     const uint32_t v = bitmap[w];
     if (!v) continue;
     for (uint32_t p = 0; p < x.fnum; ++p) {
-      uint32_t* dst = p == x.fid ? (uint32_t*) x.mrecv[par][p] : (uint32_t*) x.msend[par][p];
+      uint32_t* dst = (p == x.fid ? (uint32_t*) x.mrecv[par][p] : (uint32_t*) x.msend[par][p]) + off;
       dst[w] = v;
     }
     wrote = x.fnum > 1;
@@ -751,13 +787,13 @@ GL_DEV bool front_ship(const XComm& x, uint32_t par, const uint32_t* bitmap) {
   return wrote;
 }
 // the segments of parity `par` were consumed: back to zero for their next use (two shipments later)
-GL_DEV void front_zero(const XComm& x, uint32_t par) {
+GL_DEV void front_zero(const XComm& x, uint32_t par, uint32_t off) {
   const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
   const uint64_t gtid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t total = (uint64_t) x.fnum * x.seg_words;
   for (uint64_t i = gtid; i < total; i += nthreads) {
     const uint32_t f = (uint32_t) (i / x.seg_words), w = (uint32_t) (i % x.seg_words);
-    uint32_t* seg = (uint32_t*) x.mrecv[par][f];
+    uint32_t* seg = (uint32_t*) x.mrecv[par][f] + off;
     if (__ldcg(seg + w)) seg[w] = 0u;
   }
 }
@@ -801,6 +837,9 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
   unsigned long long n_f, m_f, visited_edges;
   uint32_t phase = ctl->r_phase;
   bool premirrored = false;
+  uint32_t gen = 0;        // frontier generations shipped by this launch (global-frontier scheme)
+  uint32_t cur_off = 0;    // word offset of the generation holding the current level's frontier
+  int cur_cached = 1;
   long long S[3];
   if (gtid == 0) ctl->x_last_tag = x.tag0 - 1;   // (same thread later records every collective)
   if (phase == 0xFFFFFFFFu) {
@@ -843,7 +882,7 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
     GL_MARK(0);
     if (nphase != 1) {
       if (premirrored && x.global_front) {
-        front_zero(x, mseq & 1);   // the speculative shipment of this frontier stays unused
+        front_zero(x, mseq & 1, cur_off);   // the speculative shipment of this frontier stays unused
         grid.sync();
       }
       premirrored = false;   // (a speculative shipment of this frontier stays unused)
@@ -855,7 +894,7 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
         ++mseq;
         if (!mirror_sync_bits(grid, x, sm.xs, tag++, mseq & 1, a.vis, ctl)) return;
       }
-      OpBfsPush op{a.vis, nxt, A.remote, a.er.rp, a.pa.ivnum};
+      OpBfsPush op{a.vis, nxt, A.remote, a.er.rp, a.pa.ivnum, a.deg8};
       GL_MARK(1);
       frontier_scan_phase<OpBfsPush>(sm.scan, cur, a.pa.ivnum, a.er, op, C, a.hubs, a.hub_cap, a.hub_deg, acc);
       grid.sync();
@@ -905,20 +944,28 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
         if (!premirrored) {
           // the frontier came out of a push level: replicate my segment of it now
           ++mseq;
-          const bool wrote0 = front_ship(x, mseq & 1, cur);
+          cur_off = ((gen >> 1) % x.seg_gens) * x.seg_stride;
+          cur_cached = (gen >> 1) < x.seg_gens;
+          ++gen;
+          const bool wrote0 = front_ship(x, mseq & 1, cur_off, cur);
           long long dummy[3];
           if (!xsync(grid, x, sm.xs, tag++, -1, nullptr, 0, 0, ctl, dummy, wrote0)) return;
         }
         GL_MARK(1);
         PullArgs pa = a.pa;
         pa.seg = (const uint32_t* const*) x.mrecv[mseq & 1];   // every owner's segment of this level's frontier
+        pa.seg_off = cur_off;
+        pa.seg_cached = cur_cached;
         bfs_pull_phase(sm.pull, pa, cur, a.vis, nxt, C, acc);
         flush_acc(acc, C);
         grid.sync();
         GL_MARK(2);
-        front_zero(x, mseq & 1);            // consumed; this parity is written again two shipments from now
+        front_zero(x, mseq & 1, cur_off);   // consumed: zero again for a later query / a wrapped generation
         ++mseq;
-        const bool wrote = front_ship(x, mseq & 1, nxt);   // next level's frontier rides with the statistics
+        cur_off = ((gen >> 1) % x.seg_gens) * x.seg_stride;
+        cur_cached = (gen >> 1) < x.seg_gens;
+        ++gen;
+        const bool wrote = front_ship(x, mseq & 1, cur_off, nxt);   // next level's frontier rides with the statistics
         if (!xsync(grid, x, sm.xs, tag++, -1, C, 0, 0, ctl, S, wrote)) return;
         premirrored = true;
         GL_MARK(4);
@@ -1045,7 +1092,7 @@ struct BfsApp : gl_app {
   uint32_t* nz_in = nullptr;   // directed: inner vertices with in-degree > 0
   // several fragments, fused kernel: gid-space copies for the replicated global frontier
   uint32_t *gcol = nullptr, *hub_nbr_g = nullptr;
-  uint32_t seg_words = 0;
+  uint32_t seg_words = 0, seg_stride = 0, seg_gens = 1;
   bool global_front = false;
   uint32_t *perm = nullptr, *order = nullptr, *nz_p = nullptr, *col_p = nullptr;
   uint64_t* rp_p = nullptr;
@@ -1083,6 +1130,8 @@ struct BfsApp : gl_app {
     cudaFree(gcol);
     cudaFree(hub_nbr_g);
     cudaFree(d_out8);
+    cudaFree(deg8);
+    if (ev_done) cudaEventDestroy(ev_done);
     if (h_out8) cudaFreeHost(h_out8);
     for (auto e : ev8)
       if (e) cudaEventDestroy(e);
@@ -1131,6 +1180,10 @@ struct BfsApp : gl_app {
       g_col = col_p;
       g_nz = nz_p;
     }
+    if (fv.ivnum && cfg.direction_opt) {
+      GL_CUDA(cudaMalloc(&deg8, fv.ivnum));
+      GL_LAUNCH(k_bfs_deg8, (fv.ivnum + 255) / 256, 256, eng.stream, g_rp, fv.ivnum, deg8);
+    }
     p_rp = g_rp;
     p_col = g_col;
     if (fv.directed && can_pull()) {
@@ -1178,7 +1231,24 @@ struct BfsApp : gl_app {
       long long mw = (long long) bm_words(fv.ivnum), unused = 0;
       GL_TRY(mm.PeerAllReduce(eng.stream, &mw, &unused, &c, 2));
       seg_words = (uint32_t) mw;
-      global_front = can_pull() && cfg.reserved[7] == 0 && (size_t) seg_words * 4 <= comm->mirror_bytes;
+      // a mirror slot (8 B per inner vertex) holds many 1-bit-per-vertex segments: one GENERATION per pull
+      // level, so that a level's frontier bits sit at addresses no SM has cached yet (front_test)
+      seg_stride = (seg_words + 63) & ~63u;
+      seg_gens = (uint32_t) std::min<size_t>(32, seg_stride ? comm->mirror_bytes / ((size_t) seg_stride * 4) : 0);
+      global_front = can_pull() && cfg.reserved[7] == 0 && seg_gens >= 2;
+      if (can_pull() && fv.ivnum + fv.ovnum) {
+        // the hub-neighbour prefilter should pick the true highest-degree neighbour, also when it is an
+        // outer copy: owners' degrees reach the ghosts through one dense mirror sync (collective)
+        uint32_t* deg32 = nullptr;
+        GL_CUDA(cudaMalloc(&deg32, sizeof(uint32_t) * (size_t) tvnum));
+        GL_LAUNCH(k_bfs_deg32, (tvnum + 255) / 256, 256, eng.stream, fv.oe_rp, fv.ivnum, tvnum, deg32);
+        GL_TRY(mm.SyncValuesToGhosts(eng.stream, deg32, 4));
+        if (fv.ivnum) GL_LAUNCH(k_bfs_hub_nbr, eng.sm_count * 8, 256, eng.stream, p_rp, row_end(), p_col, fv.ivnum, hub_nbr, deg32);
+        GL_CUDA(cudaStreamSynchronize(eng.stream));
+        cudaFree(deg32);
+      } else if (can_pull()) {
+        GL_TRY(mm.SyncValuesToGhosts(eng.stream, nullptr, 4));   // keep the collective sequence identical on every rank
+      }
       if (global_front) {
         const uint64_t m = (fv.directed ? frag->ie.entries : frag->oe.entries);
         const uint32_t gid0 = fv.fid << fv.fid_offset;
@@ -1209,7 +1279,7 @@ struct BfsApp : gl_app {
       GL_TRY(mm.PeerBarrier(s));
       for (int par = 0; par < 2; ++par)
         for (uint32_t f = 0; f < fv.fnum; ++f)
-          GL_CUDA(cudaMemsetAsync(comm->local_base + comm->mirror_off(par, f), 0, (size_t) seg_words * 4, s));
+          GL_CUDA(cudaMemsetAsync(comm->local_base + comm->mirror_off(par, f), 0, (size_t) seg_stride * 4 * seg_gens, s));
       GL_CUDA(cudaStreamSynchronize(s));
       GL_TRY(mm.PeerBarrier(s));
       comm->mirror_dirty = false;
@@ -1277,6 +1347,7 @@ struct BfsApp : gl_app {
     a.hubs = eng.hubs;
     a.hub_cap = eng.hub_cap;
     a.hub_deg = eng.hub_deg;
+    a.deg8 = deg8;
     // measured (profiles/r02_tma_hub_ab.txt): inside the fused kernel the TMA-staged hub phase is SLOWER
     // (0.221 vs 0.179 ms per query) -- opt-in only; the stand-alone k_hub_scan_tma is the default elsewhere
     a.hub_tma = (getenv("GL_HUB_TMA") && atoi(getenv("GL_HUB_TMA")) == 2) ? 1 : 0;
@@ -1307,6 +1378,8 @@ struct BfsApp : gl_app {
       x.global_front = global_front ? 1 : 0;
       x.seg_words = seg_words;
       x.my_words = (uint32_t) bm_words(fv.ivnum);
+      x.seg_stride = seg_stride;
+      x.seg_gens = seg_gens;
       if (global_front) {
         a.pa.col = gcol;
         a.pa.hub_nbr = hub_nbr_g;
@@ -1338,6 +1411,8 @@ struct BfsApp : gl_app {
       }
       GL_COUNT_LAUNCH();
       GL_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(BfsFusedCtl), cudaMemcpyDeviceToHost, s));
+      if (!ev_done) GL_CUDA(cudaEventCreate(&ev_done));
+      GL_CUDA(cudaEventRecord(ev_done, s));   // the query's last device operation (overwritten by a relaunch after a spill)
       GL_CUDA(cudaStreamSynchronize(s));
       if (multi) {
         comm->seq_base = h_ctl->x_last_tag;
@@ -1375,6 +1450,7 @@ struct BfsApp : gl_app {
       note_step(h_ctl->stat[i].scanned, h_ctl->stat[i].frontier, (int) h_ctl->stat[i].mode);
     // every GPU left the kernel on the same all-reduced "frontier is empty": no round vote needed
     mm.decided_terminate = true;
+    query_end = ev_done;
     return GL_OK;
   }
 
@@ -1515,6 +1591,8 @@ struct BfsApp : gl_app {
   // compact result path: u8 depths, chunked D2H into pinned staging, widened to
   // the reference's int64 (bfs_context.h:31 depth_type) by host threads while the
   // next chunk is still crossing PCIe
+  cudaEvent_t ev_done = nullptr;
+  uint8_t* deg8 = nullptr;
   uint8_t *d_out8 = nullptr, *h_out8 = nullptr;
   cudaEvent_t ev8[8] = {};
   int ResultCompact(int64_t* host_out, uint32_t nl) {

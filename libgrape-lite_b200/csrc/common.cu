@@ -48,6 +48,7 @@ struct L2Cfg {
   int device = -1;
   size_t persist_max = 0, window_max = 0;
   bool enabled = true;
+  bool carved = false;   // the persisting set-aside is currently taken out of the L2
 };
 L2Cfg* l2cfg() {
   static thread_local L2Cfg c;
@@ -61,10 +62,7 @@ L2Cfg* l2cfg() {
     c.window_max = (size_t) p.accessPolicyMaxWindowSize;
     const char* e = getenv("GL_L2_PERSIST");
     c.enabled = !(e && atoi(e) == 0) && c.persist_max > 0 && c.window_max > 0;
-    if (c.enabled && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c.persist_max) != cudaSuccess) {
-      cudaGetLastError();
-      c.enabled = false;
-    }
+    c.carved = false;
   }
   return &c;
 }
@@ -73,6 +71,17 @@ L2Cfg* l2cfg() {
 int l2_persist_window(cudaStream_t s, const void* ptr, size_t bytes) {
   L2Cfg* c = l2cfg();
   if (!c || !c->enabled || !ptr || !bytes) return GL_OK;
+  // The set-aside is carved out of the L2 for EVERY kernel of the device, also for apps that install
+  // no window (measured: PageRank's atomic push drops from 7.0 to 9.6 ms per round while it is taken):
+  // it is taken only while a window is installed and given back by l2_persist_clear.
+  if (!c->carved) {
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->persist_max) != cudaSuccess) {
+      cudaGetLastError();
+      c->enabled = false;
+      return GL_OK;
+    }
+    c->carved = true;
+  }
   cudaStreamAttrValue a;
   memset(&a, 0, sizeof(a));
   a.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
@@ -94,6 +103,10 @@ int l2_persist_clear(cudaStream_t s) {
   a.accessPolicyWindow.num_bytes = 0;
   if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
   cudaCtxResetPersistingL2Cache();
+  if (c->carved) {
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
+    c->carved = false;
+  }
   return GL_OK;
 }
 

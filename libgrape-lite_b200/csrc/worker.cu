@@ -155,6 +155,7 @@ int gl_app_query(gl_app_t* a, gl_query_stats* stats) {
   GL_ARG(a, "null argument");
   const uint64_t launches0 = g_kernel_launches;
   a->rec.reset();
+  a->query_end = nullptr;
   a->q_entries = a->q_frontier = a->q_touched = 0;
   a->rounds = 0;
   GL_TRY(a->Init());  // context Init (gpu_worker.h:61): resets per-query state
@@ -185,7 +186,7 @@ int gl_app_query(gl_app_t* a, gl_query_stats* stats) {
     memset(stats, 0, sizeof(*stats));
     stats->supersteps = a->rounds;
     float ms = 0;
-    cudaEventElapsedTime(&ms, a->rec.ev[0], a->rec.ev[a->rec.used - 1]);
+    cudaEventElapsedTime(&ms, a->rec.ev[0], a->query_end ? a->query_end : a->rec.ev[a->rec.used - 1]);
     stats->query_ms = ms;
     stats->entries_scanned = a->q_entries;
     stats->frontier_vertices = a->q_frontier;
@@ -233,6 +234,7 @@ int gl_app_result_oids(gl_app_t* a, int64_t* host_out, size_t count) {
 
 void gl_app_destroy(gl_app_t* a) {
   if (!a) return;
+  if (a->eng.stream) l2_persist_clear(a->eng.stream);   // give the L2 set-aside back (common.cu)
   a->mm.Destroy();
   a->rec.destroy();
   a->eng.destroy();
