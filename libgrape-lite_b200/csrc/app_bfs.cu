@@ -191,9 +191,11 @@ struct PullArgs {
   int seg_cached;       // 1: these addresses were never read before in this launch -> L1 may cache them
 };
 
-// is vertex `id` in the frontier?  (segments are written by peers: L1 is bypassed)
+// is vertex `id` in the frontier?  kGlobal is a compile-time switch: the single-fragment kernels
+// keep the plain local-bitmap probe (a run-time branch here cost 8 % of the whole query)
+template <bool kGlobal>
 GL_DEV bool front_test(const PullArgs& a, const uint32_t* cur, uint32_t id) {
-  if (a.seg) {
+  if (kGlobal) {
     // A frontier bit is probed ~10^7 times per level: it must be an L1 hit.  L1 is not coherent
     // with the peers' stores, so every pull level of a launch reads a FRESH generation of the
     // segments (addresses no SM has loaded before in this launch); once the generations wrap
@@ -211,6 +213,7 @@ GL_DEV bool front_test(const PullArgs& a, const uint32_t* cur, uint32_t id) {
 // independent 16-byte loads in flight (stage 1), hands the unresolved ones to
 // a CTA-wide row scan (stage 2) and finally writes its visited / next-level
 // word with plain stores (the word belongs to this thread during the pull).
+template <bool kGlobal>
 GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
                            const uint32_t* __restrict__ cur, uint32_t* vis,
                            uint32_t* nxt, ScanCtrl* ctrl, ScanAcc& acc) {
@@ -242,10 +245,11 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
         const bool c1 = (nib & 2u) && h.y != kInfU32;
         const bool c2 = (nib & 4u) && h.z != kInfU32;
         const bool c3 = (nib & 8u) && h.w != kInfU32;
-        const uint32_t i0 = c0 ? h.x : a.hub_dummy, i1 = c1 ? h.y : a.hub_dummy;
-        const uint32_t i2 = c2 ? h.z : a.hub_dummy, i3 = c3 ? h.w : a.hub_dummy;
-        const bool t0 = front_test(a, cur, i0), t1 = front_test(a, cur, i1);
-        const bool t2 = front_test(a, cur, i2), t3 = front_test(a, cur, i3);
+        const uint32_t dummy = kGlobal ? a.hub_dummy : 0u;
+        const uint32_t i0 = c0 ? h.x : dummy, i1 = c1 ? h.y : dummy;
+        const uint32_t i2 = c2 ? h.z : dummy, i3 = c3 ? h.w : dummy;
+        const bool t0 = front_test<kGlobal>(a, cur, i0), t1 = front_test<kGlobal>(a, cur, i1);
+        const bool t2 = front_test<kGlobal>(a, cur, i2), t3 = front_test<kGlobal>(a, cur, i3);
         uint32_t r = 0;
         r |= (c0 && t0) ? 1u : 0u;
         r |= (c1 && t1) ? 2u : 0u;
@@ -283,7 +287,7 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
         bool found = false;
         uint32_t p = 0;
         for (; p < lim; ++p) {
-          if (front_test(a, cur, row[p])) {
+          if (front_test<kGlobal>(a, cur, row[p])) {
             found = true;
             ++p;
             break;
@@ -305,7 +309,7 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
         uint32_t p = kPullSerialCap;
         for (; p < len; p += 32) {
           const uint32_t q = p + lane_id();
-          const bool h = q < len && front_test(a, cur, row[q]);
+          const bool h = q < len && front_test<kGlobal>(a, cur, row[q]);
           if (__any_sync(0xffffffffu, h)) {
             hit = true;
             p += 32;
@@ -340,7 +344,7 @@ k_bfs_pull(PullArgs a, const uint32_t* __restrict__ cur, uint32_t* vis,
            uint32_t* nxt, ScanCtrl* ctrl) {
   __shared__ PullSmem sm;
   ScanAcc acc;
-  bfs_pull_phase(sm, a, cur, vis, nxt, ctrl, acc);
+  bfs_pull_phase<false>(sm, a, cur, vis, nxt, ctrl, acc);
   flush_acc(acc, ctrl);
 }
 
@@ -536,7 +540,7 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused(BfsFusedAr
       if (a.hub_tma) hub_scan_phase_tma<OpBfsPush>(sm.hub, a.er, op, C, a.hubs, a.hub_cap, acc);
       else hub_scan_phase<OpBfsPush>(&s_item, a.er, op, C, a.hubs, a.hub_cap, acc);
     } else {
-      bfs_pull_phase(sm.pull, a.pa, cur, a.vis, nxt, C, acc);
+      bfs_pull_phase<false>(sm.pull, a.pa, cur, a.vis, nxt, C, acc);
     }
     flush_acc(acc, C);
     grid.sync();
@@ -817,6 +821,9 @@ struct BfsMultiArgs {
   XComm x;
 };
 
+// kGF: replicated global frontier (round 2) / per-holder bit-compressed slices (round 1) -- two
+// instantiations, so that neither carries the other scheme's registers
+template <bool kGF>
 __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsMultiArgs A) {
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(128) union {
@@ -881,12 +888,12 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
 #define GL_MARK(k) do { if (gtid == 0 && tl < 32) ctl->ph[tl][k] = global_ns(); } while (0)
     GL_MARK(0);
     if (nphase != 1) {
-      if (premirrored && x.global_front) {
+      if (premirrored && kGF) {
         front_zero(x, mseq & 1, cur_off);   // the speculative shipment of this frontier stays unused
         grid.sync();
       }
       premirrored = false;   // (a speculative shipment of this frontier stays unused)
-      if (phase == 1 && !x.global_front) {
+      if (phase == 1 && !kGF) {
         // leaving the pull phase: outer copies learn which vertices their
         // owners visited meanwhile, so they are not reported again
         // (global-frontier scheme: skipped -- a holder may report an already visited vertex once
@@ -940,7 +947,7 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
       GL_MARK(5);
       ++msg_round;
     } else {
-      if (x.global_front) {
+      if (kGF) {
         if (!premirrored) {
           // the frontier came out of a push level: replicate my segment of it now
           ++mseq;
@@ -956,7 +963,7 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
         pa.seg = (const uint32_t* const*) x.mrecv[mseq & 1];   // every owner's segment of this level's frontier
         pa.seg_off = cur_off;
         pa.seg_cached = cur_cached;
-        bfs_pull_phase(sm.pull, pa, cur, a.vis, nxt, C, acc);
+        bfs_pull_phase<true>(sm.pull, pa, cur, a.vis, nxt, C, acc);
         flush_acc(acc, C);
         grid.sync();
         GL_MARK(2);
@@ -979,7 +986,7 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
         grid.sync();
       }
       GL_MARK(1);
-      bfs_pull_phase(sm.pull, a.pa, cur, a.vis, nxt, C, acc);
+      bfs_pull_phase<false>(sm.pull, a.pa, cur, a.vis, nxt, C, acc);
       flush_acc(acc, C);
       grid.sync();
       GL_MARK(2);
@@ -1353,7 +1360,9 @@ struct BfsApp : gl_app {
     a.hub_tma = (getenv("GL_HUB_TMA") && atoi(getenv("GL_HUB_TMA")) == 2) ? 1 : 0;
     const bool multi = fv.fnum > 1;
     if (!fused_grid)
-      fused_grid = multi ? persistent_grid(k_bfs_fused_multi, eng.sm_count) : persistent_grid(k_bfs_fused, eng.sm_count);
+      fused_grid = multi ? (global_front ? persistent_grid(k_bfs_fused_multi<true>, eng.sm_count)
+                                         : persistent_grid(k_bfs_fused_multi<false>, eng.sm_count))
+                         : persistent_grid(k_bfs_fused, eng.sm_count);
     BfsMultiArgs ma;
     if (multi) {
       ma.remote = remote;
@@ -1404,7 +1413,8 @@ struct BfsApp : gl_app {
         ma.x.msg_round0 = (uint32_t) mm.round;
         ma.x.mirror_seq0 = (uint32_t) mm.mirror_seq;
         void* args[] = {&ma};
-        GL_CUDA(cudaLaunchCooperativeKernel((void*) k_bfs_fused_multi, dim3(fused_grid), dim3(kTB), args, 0, s));
+        GL_CUDA(cudaLaunchCooperativeKernel(global_front ? (void*) k_bfs_fused_multi<true> : (void*) k_bfs_fused_multi<false>,
+                                            dim3(fused_grid), dim3(kTB), args, 0, s));
       } else {
         void* args[] = {&a};
         GL_CUDA(cudaLaunchCooperativeKernel((void*) k_bfs_fused, dim3(fused_grid), dim3(kTB), args, 0, s));
