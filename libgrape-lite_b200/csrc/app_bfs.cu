@@ -1637,7 +1637,17 @@ struct BfsApp : gl_app {
   int Result(void* host_out, size_t) override {
     if (fv.ivnum == 0) return GL_OK;
     uint32_t nl = std::min<uint32_t>(max_lv, used_lv + 1);
-    if (!spilled && depth_base == 0 && nl <= 254 && cfg.reserved[6] == 0) return ResultCompact((int64_t*) host_out, nl);
+    // The byte-wide result pays when this process has the host to itself (1.6-2.3 ms vs 2.9 ms); with
+    // several rank processes on one host the widening threads of all ranks compete for the same memory
+    // system and the plain int64 copy was measured to be as fast and far more stable (N = 2: 3.2 ms
+    // vs 2.8-6.7 ms) -- GL_RESULT_COMPACT=1/0 overrides the choice.
+    static const bool compact_ok = [] {
+      if (const char* e = getenv("GL_RESULT_COMPACT")) return atoi(e) != 0;
+      const char* lw = getenv("LOCAL_WORLD_SIZE");
+      return !(lw && atoi(lw) > 1);
+    }();
+    if (compact_ok && !spilled && depth_base == 0 && nl <= 254 && cfg.reserved[6] == 0)
+      return ResultCompact((int64_t*) host_out, nl);
     GL_LAUNCH(k_depth_from_levels, (fv.ivnum + 255) / 256, 256, eng.stream, lv, (uint32_t) words, nl, fv.ivnum, perm,
               depth_base, spilled ? spill : nullptr, out64);
     GL_CUDA(cudaMemcpyAsync(host_out, out64, sizeof(int64_t) * fv.ivnum, cudaMemcpyDeviceToHost, eng.stream));
