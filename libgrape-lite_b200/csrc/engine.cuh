@@ -282,43 +282,20 @@ GL_DEV void walk_tile(ScanSmem<typename Op::Meta>& sm, uint32_t nf, EdgeRange er
     }
     if (threadIdx.x == 0) sm.hubn = 0;
   }
-  // Every thread walks kWalkU entries per step (e0 + t, e0 + kTB + t, ...): the kWalkU owner searches
-  // (10 dependent shared-memory probes each) and the kWalkU column loads are independent chains that
-  // overlap, instead of one chain at a time.
-  constexpr int kWalkU = 4;
-  for (uint32_t e0 = 0; e0 < total; e0 += kWalkU * kTB) {
-    uint32_t lo[kWalkU], hi[kWalkU], e[kWalkU];
-#pragma unroll
-    for (int k = 0; k < kWalkU; ++k) {
-      e[k] = e0 + k * kTB + threadIdx.x;
-      lo[k] = 0;
-      hi[k] = nf;
-    }
-    // largest j with pfx[j] <= e (entries past `total` search for a clamped value and are skipped below)
-#pragma unroll 1
-    for (int it = 0; it < 11; ++it) {
-#pragma unroll
-      for (int k = 0; k < kWalkU; ++k) {
-        if (hi[k] - lo[k] > 1) {
-          const uint32_t mid = (lo[k] + hi[k]) >> 1;
-          if (sm.pfx[mid] <= e[k]) lo[k] = mid; else hi[k] = mid;
-        }
+  for (uint32_t e0 = 0; e0 < total; e0 += kTB) {
+    uint32_t e = e0 + threadIdx.x;
+    if (e < total) {
+      // largest j with pfx[j] <= e
+      uint32_t lo = 0, hi = nf;
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (sm.pfx[mid] <= e) lo = mid; else hi = mid;
       }
+      uint64_t pos = sm.rp[lo] + (e - sm.pfx[lo]);
+      uint32_t v = ld_stream_u32(er.col + pos);
+      W w = Op::kWeighted ? load_w<W>(er.w, pos) : (W) 1;
+      call_edge(op, sm.v[lo], sm.meta[lo], v, w, pos, acc);
     }
-    uint64_t pos[kWalkU];
-    uint32_t v[kWalkU];
-    W w[kWalkU];
-#pragma unroll
-    for (int k = 0; k < kWalkU; ++k) {
-      if (e[k] < total) {
-        pos[k] = sm.rp[lo[k]] + (e[k] - sm.pfx[lo[k]]);
-        v[k] = ld_stream_u32(er.col + pos[k]);
-        w[k] = Op::kWeighted ? load_w<W>(er.w, pos[k]) : (W) 1;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kWalkU; ++k)
-      if (e[k] < total) call_edge(op, sm.v[lo[k]], sm.meta[lo[k]], v[k], w[k], pos[k], acc);
   }
   if (threadIdx.x == 0) scanned += total;
   __syncthreads();
