@@ -461,6 +461,19 @@ def run_gpu(args):
     r, app, res = measure_app(G, pkg, frag, comm, kind, cfg, args.steps, args.warmup, flush, edges_fn, weighted=weighted)
     clocks = sampler.stop() if rank == 0 else None
     app.close()
+    bfs_parity = None
+    if args.app == "bfs" and not args.no_parity:
+        # the same query through an independent path of the engine: push only, one superstep per host
+        # round (k_frontier_scan + k_hub_scan, per-vertex messages between fragments), the fragment's own
+        # vertex order -- the depth arrays of all ranks must be identical (outside every timed region)
+        chk = pkg.App("bfs", frag, comm, source_oid=int(src_oid), direction_opt=0, fuse_supersteps=0, reserved={1: 1})
+        chk.query()
+        ref = chk.result()
+        chk.close()
+        mismatching_ranks = G.reduce_i64([0 if np.array_equal(ref, res) else 1])[0]
+        same = mismatching_ranks == 0
+        bfs_parity = {"check": "depths(measured configuration) == depths(push-only, stepwise, fragment order) on every rank",
+                      "parity_ok": bool(same)}
     peak, peak_src = r["_peak"]
     ms_per_step = r["ms_per_query"]
     edges = r["traversed_edges"]
@@ -497,6 +510,7 @@ def run_gpu(args):
                        % (args.app.upper(), scale, args.edgefactor, args.seed, world,
                           (", push-only" if args.push_only else ", push/pull") if args.app == "bfs" else ""),
                        "mapping": MAPPING,
+                       "parity": bfs_parity,
                        "vertices": n, "input_edges": args.edgefactor << scale,
                        "csr_entries_per_gpu": int(frag.oe_num), "traversed_edges": edges,
                        "source_oid": int(src_oid), "supersteps": r["supersteps"],
@@ -592,6 +606,7 @@ def main():
     ap.add_argument("--pr-f32", action="store_true", help="PageRank pull gathering f32 contributions (f64 sums)")
     ap.add_argument("--pr-nohub", action="store_true", help="with --pr-f32: without the shared-memory hub table (A/B)")
     ap.add_argument("--no-hub-order", action="store_true", help="disable the hub-first shadow CSR (BFS)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run BFS parity check (second app, push-only)")
     ap.add_argument("--bfs-beta", type=int, default=0, help="BFS pull->push threshold divisor (0 = library default)")
     ap.add_argument("--pr-pull", action="store_true", help="PageRank: deterministic pull step instead of atomicAdd push")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per superstep (profiling) instead of the fused query kernel")

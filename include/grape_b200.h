@@ -409,7 +409,9 @@ typedef struct {
                             0 = one superstep per host round                    */
   int reserved[8];       /* tuning / test hooks, 0 = default:
                             [0] 1: WCC dense rounds as pull sweeps
-                            [1] 1: BFS without the hub-first shadow CSR
+                            [1] 1: BFS without the hub-first shadow CSR; 2: with it also on a
+                                   small graph (default: from 2^16 vertices on); 3: like 2, several
+                                   fragments, without the delegated-hub lists (A/B)
                             [2] BFS pull->push threshold divisor (default 24)
                             [3] >=4: number of BFS level bitmaps (forces spills)
                             [4] 1: PageRank f32 pull without the shared-memory hub table (A/B)

@@ -87,6 +87,8 @@ int build_hub_order(cudaStream_t s, const uint64_t* rp, uint32_t n, uint32_t** p
 int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, uint64_t m, uint32_t n,
                        const uint32_t* order, const uint32_t* perm, uint64_t** rp_out, uint32_t** col_out,
                        const void* w4 = nullptr, void** w4_out = nullptr, bool sort_rows = true);
+// every row [rp[i], rp[i+1]) of *col sorted ascending (the array is replaced by a sorted copy)
+int sort_csr_rows(cudaStream_t s, const uint64_t* rp, uint32_t n, uint64_t m, uint32_t** col);
 gl_app* make_bfs();
 gl_app* make_sssp_f32();
 gl_app* make_sssp_f64();

@@ -60,6 +60,65 @@ struct OpBfsPush {
     const uint32_t k = deg8[v];
     return k == 0 ? 0ull : (k == 1 ? 1ull : (3ull << (k - 2)));
   }
+  // Hub rows, 32 consecutive entries per call (engine.cuh, has_warp_entries).  The rows of the
+  // hub-first shadow graph are sorted, so neighbouring lanes mostly hit the same bitmap word: the
+  // lanes of a run of equal words OR their bits together and the run's last lane issues ONE atomicOr
+  // per bitmap instead of one per entry (the source hub of a scale-24 R-MAT graph has 7e5 entries
+  // over 2e4 words).  Exactly the per-entry semantics: a bit counts for the first lane of the run
+  // that carries it, and only if the word did not hold it before.
+  static constexpr bool kWarpEntries = true;
+  GL_DEV void warp_edge(uint32_t v, bool valid, ScanAcc& acc) const {
+    const uint32_t lane = lane_id();
+    const uint32_t w = v >> 5;
+    uint32_t bit = 0;
+    if (valid) {
+      bit = 1u << (v & 31);
+      bit &= ~vis[w];                    // plain (possibly stale) read first
+    }
+    if (!__any_sync(0xffffffffu, bit != 0)) return;
+    // runs of lanes with the same word (invalid / already-visited lanes join their neighbours' runs
+    // with an empty bit set, or form runs of their own that end without an atomic)
+    const uint32_t wp = __shfl_up_sync(0xffffffffu, w, 1);
+    const bool head = lane == 0 || wp != w;
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const uint32_t seg = __popc(heads & (0xFFFFFFFFu >> (31 - lane)));
+    uint32_t incl = bit;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      const uint32_t so = __shfl_up_sync(0xffffffffu, seg, o);
+      if (lane >= (uint32_t) o && so == seg) incl |= t;
+    }
+    const uint32_t prev_incl = __shfl_up_sync(0xffffffffu, incl, 1);
+    const uint32_t excl = head ? 0u : prev_incl;
+    const uint32_t tails = (heads >> 1) | 0x80000000u;
+    const bool tail = (tails >> lane) & 1u;
+    uint32_t old = 0;
+    if (tail && incl) {
+      old = atomicOr(vis + w, incl);
+      const uint32_t fresh = incl & ~old;
+      if (fresh) {
+        atomicOr(nxt + w, fresh);        // level bitmap of depth+1 (also for outer v)
+        // outer copies (lid >= ivnum) are reported to their owners
+        const uint32_t lo = w << 5;
+        uint32_t outer = 0;
+        if (lo >= ivnum) outer = 0xFFFFFFFFu;
+        else if (lo + 32 > ivnum) outer = 0xFFFFFFFFu << (ivnum - lo);
+        if (fresh & outer) atomicOr(remote + w, fresh & outer);
+      }
+    }
+    const uint32_t mytail = lane + __ffs(tails >> lane) - 1;
+    old = __shfl_sync(0xffffffffu, old, mytail);
+    if (bit & ~old & ~excl) {
+      acc.touched++;
+      if (v < ivnum) {
+        acc.next_count++;
+        acc.next_edges += degree_of(v);
+      } else {
+        acc.remote++;
+      }
+    }
+  }
   GL_DEV void edge(uint32_t, Meta, uint32_t v, W, ScanAcc& acc) const {
     if (bit_test(vis, v)) return;        // plain (possibly stale) read first
     if (!bit_set_atomic(vis, v)) return; // somebody else won
@@ -110,6 +169,54 @@ __global__ void k_bfs_gid_table(const uint32_t* __restrict__ lids, uint32_t n, u
   if (i >= n) return;
   const uint32_t c = lids[i];
   out[i] = c == kInfU32 ? kInfU32 : (c < ivnum ? (my_gid0 | c) : ovgid[c - ivnum]);
+}
+
+// several fragments, hub-first order: the gid of outer copy o in its owner's NEW lid space
+__global__ void k_bfs_ovgid_new(const uint32_t* __restrict__ ovgid, const uint32_t* __restrict__ newlid, uint32_t ovnum,
+                                uint32_t id_mask, uint32_t* out) {
+  const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < ovnum) out[o] = (ovgid[o] & ~id_mask) | (newlid[o] & id_mask);
+}
+// gid <-> row-sort key (lid = degree rank inside the owner fragment in the high bits, fid in the low
+// bits): rows sorted by this key list the likeliest parents first, whichever fragment owns them
+__global__ void k_bfs_gid_key(uint32_t* g, uint64_t m, int fid_offset, uint32_t id_mask, int to_key) {
+  const int fid_bits = 32 - fid_offset;
+  for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t) gridDim.x * blockDim.x) {
+    const uint32_t x = g[i];
+    g[i] = to_key ? (((x & id_mask) << fid_bits) | (x >> fid_offset))
+                  : (((x & ((1u << fid_bits) - 1u)) << fid_offset) | (x >> fid_bits));
+  }
+}
+// Delegated hubs (several fragments, hub-first order): the kDlgPerFrag highest-ranked vertices of
+// EVERY fragment are known to all GPUs by gid, and every GPU keeps, per hub, the list of its own
+// inner vertices adjacent to it (the hub's row restricted to this fragment, read off the local
+// rows: in a row sorted by the lid-major key the hub entries come first).  A BFS that starts at
+// such a hub then runs level 0 on all GPUs at once, without a single message -- instead of one
+// GPU walking a 10^6-entry row and shipping most of it to the others.
+constexpr uint32_t kDlgPerFrag = 16;
+// mode 0: count[h]++ ; mode 1: list[off[h] + cursor[h]++] = v
+__global__ void k_bfs_dlg_scan(const uint64_t* __restrict__ rp, const uint32_t* __restrict__ gcol, uint32_t ivnum,
+                               int fid_offset, uint32_t id_mask, uint32_t* cnt, const uint64_t* __restrict__ off,
+                               uint32_t* list, int mode) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= ivnum) return;
+  const uint64_t b = rp[v], e = rp[v + 1];
+  uint32_t prev = kInfU32;
+  for (uint64_t p = b; p < e; ++p) {
+    const uint32_t g = gcol[p];
+    const uint32_t l = g & id_mask;
+    if (l >= kDlgPerFrag) break;
+    if (g == prev) continue;   // parallel edges
+    prev = g;
+    const uint32_t h = (g >> fid_offset) * kDlgPerFrag + l;
+    const uint32_t at = atomicAdd(cnt + h, 1u);
+    if (mode) list[off[h] + at] = v;
+  }
+}
+
+__global__ void k_bfs_first_col(const uint64_t* __restrict__ rp, const uint32_t* __restrict__ col, uint32_t n, uint32_t* out) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) out[v] = rp[v + 1] > rp[v] ? col[rp[v]] : kInfU32;
 }
 
 __global__ void k_bfs_deg32(const uint64_t* __restrict__ rp, uint32_t ivnum, uint32_t tvnum, uint32_t* deg) {
@@ -189,6 +296,13 @@ struct PullArgs {
   uint32_t hub_dummy;   // a valid id for the branch-free probes of non-candidates (lid 0 / my gid 0)
   uint32_t seg_off;     // word offset of this level's generation inside every segment slot
   int seg_cached;       // 1: these addresses were never read before in this launch -> L1 may cache them
+  // Shipment of the NEXT frontier fused into the pull: a thread that finished its word stores it
+  // straight into every fragment's next-generation segment (ship_send[p] = my slot at peer p,
+  // ship_recv[ship_fid] = my own copy), so the NVLink stores drain while the pull is still running
+  // instead of in a pass of their own after it.  null: no shipment.
+  char* const* ship_send;
+  const char* const* ship_recv;
+  uint32_t ship_fid, ship_fnum, ship_off;
 };
 
 // is vertex `id` in the frontier?  kGlobal is a compile-time switch: the single-fragment kernels
@@ -214,13 +328,14 @@ GL_DEV bool front_test(const PullArgs& a, const uint32_t* cur, uint32_t id) {
 // a CTA-wide row scan (stage 2) and finally writes its visited / next-level
 // word with plain stores (the word belongs to this thread during the pull).
 template <bool kGlobal>
-GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
+GL_DEV bool bfs_pull_phase(PullSmem& sm, const PullArgs& a,
                            const uint32_t* __restrict__ cur, uint32_t* vis,
                            uint32_t* nxt, ScanCtrl* ctrl, ScanAcc& acc) {
   const uint32_t nwords = (a.ivnum + 31) / 32;
   uint64_t scanned = 0;
   uint32_t cand = 0;
   uint32_t st;
+  bool shipped = false;
   if (threadIdx.x == 0) sm.nlong = 0;
   __syncthreads();
   while (next_super_tile(sm, &ctrl->tile_ticket, a.ivnum,
@@ -329,6 +444,13 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
     if (found_w && wi < nwords) {
       vis[wi] |= found_w;  // the word is owned by this thread during the pull
       nxt[wi] = found_w;
+      if (kGlobal && a.ship_send) {
+        for (uint32_t p = 0; p < a.ship_fnum; ++p) {
+          uint32_t* dst = (p == a.ship_fid ? (uint32_t*) a.ship_recv[p] : (uint32_t*) a.ship_send[p]) + a.ship_off;
+          dst[wi] = found_w;
+        }
+        shipped = a.ship_fnum > 1;
+      }
     }
     acc.next_count += __popc(found_w);
     __syncthreads();
@@ -337,6 +459,7 @@ GL_DEV void bfs_pull_phase(PullSmem& sm, const PullArgs& a,
   unsigned long long s = warp_sum((unsigned long long) scanned);
   if (lane_id() == 0 && s) atomicAdd(&ctrl->scanned, s);
   if (threadIdx.x == 0 && cand) atomicAdd(&ctrl->frontier, (unsigned long long) cand);
+  return shipped;
 }
 
 __global__ void __launch_bounds__(kTB, 4)
@@ -362,7 +485,7 @@ struct BfsLevelStat {
 struct BfsFusedCtl {
   ScanCtrl c[3];       // rotating per-level counters (level d uses c[d % 3])
   uint32_t levels;     // levels executed
-  uint32_t has_src;
+  uint32_t has_src, src_lid;
   uint32_t overflow;   // ran out of level bitmaps
   uint32_t pad;
   unsigned long long src_deg, m_total, touched;
@@ -382,6 +505,8 @@ struct BfsFusedCtl {
   unsigned long long x_items;   // items this GPU sent
   unsigned long long ph[32][6];
   unsigned long long xw[32][2];  // GL_TRACE: per level: peer wait / first grid.sync of its last xsync
+  unsigned long long r_visited_cnt_g;    // several fragments: vertices visited so far in the whole graph (resume state)
+  unsigned long long t_kstart, t_kend;   // GL_TRACE: first / last instruction of the fused multi-fragment kernel (thread 0)
   unsigned long long xt[8];      // GL_TRACE: timestamps inside the most recent xsync (block 0, thread 0)   // GL_TRACE: phase timestamps of the first 32 levels (thread 0)
   uint32_t x_error, x_pad;   // 1 = a peer did not show up in time, 2 = landing slot overflow
   BfsLevelStat stat[kMaxFusedStats];
@@ -433,11 +558,13 @@ __global__ void k_bfs_seed_fused(uint32_t src, int has_src, uint32_t* lv0,
     deg = rp[src + 1] - rp[src];
   }
   ctl->has_src = has_src;
+  ctl->src_lid = src;
   ctl->src_deg = deg;
   ctl->r_nf = has_src ? 1 : 0;
   ctl->r_mf = deg;
   ctl->r_visited_edges = deg;
   ctl->r_visited_cnt = has_src ? 1 : 0;
+  ctl->r_visited_cnt_g = 1;
   ctl->r_phase = 0xFFFFFFFFu;
   ctl->x_error = 0;
   ctl->x_items = 0;
@@ -617,6 +744,7 @@ struct XComm {
   int global_front;
   uint32_t seg_words, my_words;
   uint32_t seg_stride, seg_gens;   // words between two generations inside a slot; generations per parity
+  int cta_fence;                   // 1: per-CTA fence.sys before a collective (see xsync)
 };
 
 struct XSmem {
@@ -648,13 +776,14 @@ GL_DEV unsigned long long x_stamp(unsigned long long tag) { return (0x4000ull | 
 
 GL_DEV bool xsync(cg::grid_group& grid, const XComm& x, XSmem& xs, unsigned long long tag,
                   int publish_par, const ScanCtrl* C, long long e0, long long e1,
-                  BfsFusedCtl* ctl, long long out[3], bool peer_stores = true) {
-  if (__syncthreads_or(peer_stores ? 1 : 0)) {
-    // the CTA's peer stores (items, mirror words) must be visible system-wide
-    // before the stamp: bar.sync makes them happen-before thread 0's fence, which
-    // is cumulative (one fence.sys per CTA instead of one per thread: a
-    // fence.sys from every thread cost ~15 us per collective)
-    // (~7 us: only CTAs that actually stored to a peer since the last collective pay it)
+                  BfsFusedCtl* ctl, long long out[3], bool peer_stores = true, long long e2 = 0) {
+  // The grid's peer stores (items, frontier words) must be visible system-wide before the stamps.
+  // x.cta_fence = 0 (default): they happen-before block 0's fence.sys below through grid.sync()
+  // (bar.sync + fence.gpu + barrier atomics: release/acquire at gpu scope), and fences are cumulative
+  // in the PTX memory model -- ONE fence.sys per stamped word instead of one per CTA (fence.sys does
+  // not scale: one per thread cost ~15 us per collective, one per storing CTA ~7-12 us).
+  // x.cta_fence = 1 (GL_XSYNC_CTA_FENCE=1): every CTA that stored to a peer fences for itself first.
+  if (x.cta_fence && __syncthreads_or(peer_stores ? 1 : 0)) {
     if (threadIdx.x == 0) __threadfence_system();
   }
   const bool tr = blockIdx.x == 0 && threadIdx.x == 0;
@@ -676,7 +805,7 @@ GL_DEV bool xsync(cg::grid_group& grid, const XComm& x, XSmem& xs, unsigned long
     }
     __syncthreads();
     if (p < x.fnum) {
-      unsigned long long i0 = (unsigned long long) e0, i1 = (unsigned long long) e1, i2 = 0;
+      unsigned long long i0 = (unsigned long long) e0, i1 = (unsigned long long) e1, i2 = (unsigned long long) e2;
       if (C) {
         const volatile ScanCtrl* VC = C;
         i0 = VC->next_count;
@@ -685,7 +814,7 @@ GL_DEV bool xsync(cg::grid_group& grid, const XComm& x, XSmem& xs, unsigned long
       }
       const unsigned long long st = x_stamp(tag), vm = 0xFFFFFFFFFFFFull;
       PeerSlot* dst = x.slot_at_peer[tag & 1][p];
-      if (publish_par >= 0) __threadfence_system();   // my count cell before my stamp
+      __threadfence_system();   // the grid's peer stores and my count cell before my stamp
       st_relaxed_sys_u64((unsigned long long*) &dst->i0, st | (i0 & vm));
       st_relaxed_sys_u64((unsigned long long*) &dst->i1, st | (i1 & vm));
       st_relaxed_sys_u64((unsigned long long*) &dst->i2, st | (i2 & vm));
@@ -817,7 +946,9 @@ struct BfsMultiArgs {
   uint32_t* remote;
   uint32_t ovnum;
   const uint32_t* ovgid;
-  unsigned long long g_m_total, g_vnum;
+  unsigned long long g_m_total, g_vnum, g_nz_total;
+  const uint32_t* dlg_list;   // delegated hubs (null: none)
+  const uint64_t* dlg_off;
   XComm x;
 };
 
@@ -842,19 +973,29 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
   unsigned long long tag = x.tag0;
   uint32_t msg_round = x.msg_round0, mseq = x.mirror_seq0;
   unsigned long long n_f, m_f, visited_edges;
+  unsigned long long visited_cnt = ctl->r_visited_cnt_g;   // whole graph (an upper bound: re-reported outer hits count twice)
   uint32_t phase = ctl->r_phase;
   bool premirrored = false;
+  uint32_t hub_src = 0;    // first launch of a query whose source is delegated hub (hub_src - 1)
   uint32_t gen = 0;        // frontier generations shipped by this launch (global-frontier scheme)
   uint32_t cur_off = 0;    // word offset of the generation holding the current level's frontier
   int cur_cached = 1;
   long long S[3];
-  if (gtid == 0) ctl->x_last_tag = x.tag0 - 1;   // (same thread later records every collective)
+  if (gtid == 0) {
+    ctl->x_last_tag = x.tag0 - 1;   // (same thread later records every collective)
+    ctl->t_kstart = global_ns();
+  }
   if (phase == 0xFFFFFFFFu) {
     // first launch of the query: the source's owner contributes (1, deg)
-    if (!xsync(grid, x, sm.xs, tag++, -1, nullptr, (long long) ctl->r_nf, (long long) ctl->r_mf, ctl, S)) return;
+    // ... and, when the source is one of the delegated hubs, its index + 1 (everybody else adds 0)
+    long long e2 = 0;
+    if (A.dlg_list && ctl->has_src && ctl->src_lid < kDlgPerFrag) e2 = (long long) (x.fid * kDlgPerFrag + ctl->src_lid) + 1;
+    if (!xsync(grid, x, sm.xs, tag++, -1, nullptr, (long long) ctl->r_nf, (long long) ctl->r_mf, ctl, S, true, e2)) return;
+    hub_src = (uint32_t) S[2];
     n_f = (unsigned long long) S[0];
     m_f = (unsigned long long) S[1];
     visited_edges = m_f;
+    visited_cnt = n_f;
     phase = 0;
   } else {
     n_f = ctl->r_nf;
@@ -869,6 +1010,7 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
         ctl->p_mf = m_f;
         ctl->p_visited_edges = visited_edges;
         ctl->p_visited_cnt = 0;
+        ctl->r_visited_cnt_g = visited_cnt;
         ctl->p_phase = phase;
       }
       break;
@@ -878,8 +1020,15 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
     uint32_t nphase = 0;
     if (!a.direction_opt) nphase = 0;
     else if (phase == 0) nphase = (m_f > m_u / 14) ? 1u : 0u;
-    else if (phase == 1) nphase = (n_f >= A.g_vnum / a.beta) ? 1u : 2u;
-    else nphase = 2;
+    else if (phase == 1) {
+      // as on one GPU (bfs_next_phase): keep pulling while the frontier is large, or -- global-frontier
+      // scheme, whose pull levels exchange no per-vertex messages -- while few candidates remain per
+      // frontier vertex; a push level after the pulls re-reports every outer neighbour of its frontier
+      const unsigned long long unvis = A.g_nz_total > visited_cnt ? A.g_nz_total - visited_cnt : 0;
+      // ... or in absolute terms (the tail of the query: a pull over < V/64 candidates costs less than a
+      // push level's pack + message round + apply)
+      nphase = (n_f >= A.g_vnum / a.beta) ? 1u : ((kGF && (unvis <= 64ull * n_f || unvis <= A.g_vnum / 64)) ? 1u : 2u);
+    } else nphase = 2;
     ScanCtrl* C = &ctl->c[depth % 3];
     uint32_t* cur = a.lv + (size_t) depth * a.words;
     uint32_t* nxt = a.lv + (size_t) (depth + 1) * a.words;
@@ -887,7 +1036,44 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
     const uint32_t tl = a.depth_base + depth;
 #define GL_MARK(k) do { if (gtid == 0 && tl < 32) ctl->ph[tl][k] = global_ns(); } while (0)
     GL_MARK(0);
-    if (nphase != 1) {
+    if (hub_src && depth == 0) {
+      // level 0 from a delegated hub: every GPU marks its own neighbours of the source out of its
+      // local list; nothing to pack, ship or apply
+      OpBfsPush op{a.vis, nxt, A.remote, a.er.rp, a.pa.ivnum, a.deg8};
+      const uint64_t b = A.dlg_off[hub_src - 1], e = A.dlg_off[hub_src];
+      for (uint64_t i = b + gtid; i < e; i += nthreads) {
+        const uint32_t v = A.dlg_list[i];
+        if (bit_set_atomic(a.vis, v)) {
+          bit_set_atomic(nxt, v);
+          acc.touched++;
+          acc.next_count++;
+          acc.next_edges += op.degree_of(v);
+        }
+      }
+      if (gtid == 0) {
+        atomicAdd(&C->scanned, (unsigned long long) (e - b));
+        if (ctl->has_src) atomicAdd(&C->frontier, 1ull);
+      }
+      flush_acc(acc, C);
+      GL_MARK(1);
+      bool wrote = false;
+      if (kGF) {
+        // a hub's neighbourhood is almost always followed by a pull level: its frontier words ride with
+        // this level's statistics collective (a push level next zeroes the unused shipment, as after a pull)
+        grid.sync();   // the words of nxt are final
+        ++mseq;
+        cur_off = ((gen >> 1) % x.seg_gens) * x.seg_stride;
+        cur_cached = (gen >> 1) < x.seg_gens;
+        ++gen;
+        wrote = front_ship(x, mseq & 1, cur_off, nxt);
+        premirrored = true;
+      }
+      GL_MARK(2);
+      GL_MARK(3);
+      if (!xsync(grid, x, sm.xs, tag++, -1, C, 0, 0, ctl, S, wrote)) return;
+      GL_MARK(4);
+      GL_MARK(5);
+    } else if (nphase != 1) {
       if (premirrored && kGF) {
         front_zero(x, mseq & 1, cur_off);   // the speculative shipment of this frontier stays unused
         grid.sync();
@@ -963,17 +1149,26 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
         pa.seg = (const uint32_t* const*) x.mrecv[mseq & 1];   // every owner's segment of this level's frontier
         pa.seg_off = cur_off;
         pa.seg_cached = cur_cached;
-        bfs_pull_phase<true>(sm.pull, pa, cur, a.vis, nxt, C, acc);
+        // the next level's frontier is shipped word by word out of the pull itself (into the next
+        // generation of the other parity) and becomes visible with the statistics collective
+        const uint32_t nxt_off = ((gen >> 1) % x.seg_gens) * x.seg_stride;
+        const int nxt_cached = (gen >> 1) < x.seg_gens;
+        pa.ship_send = x.msend[(mseq + 1) & 1];
+        pa.ship_recv = x.mrecv[(mseq + 1) & 1];
+        pa.ship_fid = x.fid;
+        pa.ship_fnum = x.fnum;
+        pa.ship_off = nxt_off;
+        const bool wrote = bfs_pull_phase<true>(sm.pull, pa, cur, a.vis, nxt, C, acc);
         flush_acc(acc, C);
-        grid.sync();
         GL_MARK(2);
-        front_zero(x, mseq & 1, cur_off);   // consumed: zero again for a later query / a wrapped generation
-        ++mseq;
-        cur_off = ((gen >> 1) % x.seg_gens) * x.seg_stride;
-        cur_cached = (gen >> 1) < x.seg_gens;
-        ++gen;
-        const bool wrote = front_ship(x, mseq & 1, cur_off, nxt);   // next level's frontier rides with the statistics
         if (!xsync(grid, x, sm.xs, tag++, -1, C, 0, 0, ctl, S, wrote)) return;
+        // every CTA of this GPU is past the pull (xsync's barriers): the consumed generation goes back
+        // to zero for a later query / a wrapped generation; nobody reads it before a later barrier
+        front_zero(x, mseq & 1, cur_off);
+        ++mseq;
+        cur_off = nxt_off;
+        cur_cached = nxt_cached;
+        ++gen;
         premirrored = true;
         GL_MARK(4);
       } else {
@@ -1026,7 +1221,9 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
     n_f = (unsigned long long) (S[0] + S[1]);
     m_f = (unsigned long long) S[2];
     visited_edges += m_f;
+    visited_cnt += n_f;
   }
+  if (gtid == 0) ctl->t_kend = global_ns();
 }
 
 struct BfsApply {
@@ -1099,6 +1296,10 @@ struct BfsApp : gl_app {
   uint32_t* nz_in = nullptr;   // directed: inner vertices with in-degree > 0
   // several fragments, fused kernel: gid-space copies for the replicated global frontier
   uint32_t *gcol = nullptr, *hub_nbr_g = nullptr;
+  uint32_t* dlg_list = nullptr;   // delegated hubs: my inner neighbours of hub h = dlg_list[dlg_off[h] .. dlg_off[h + 1])
+  uint64_t* dlg_off = nullptr;
+  uint32_t* ovgid_p = nullptr;   // hub-first order over several fragments: the outer copies' gids in the owners' new lid space
+  bool hub_multi = false;
   uint32_t seg_words = 0, seg_stride = 0, seg_gens = 1;
   bool global_front = false;
   uint32_t *perm = nullptr, *order = nullptr, *nz_p = nullptr, *col_p = nullptr;
@@ -1113,7 +1314,7 @@ struct BfsApp : gl_app {
   uint32_t curr_depth = 0;
   // frontier statistics driving the push/pull switch (stepwise path)
   uint64_t n_f = 0, m_f = 0, visited_edges = 0;
-  uint64_t g_m_total = 0, g_vnum = 0;   // whole-graph totals (all fragments)
+  uint64_t g_m_total = 0, g_vnum = 0, g_nz_total = 0;   // whole-graph totals (all fragments)
   uint32_t phase = 0;
   BfsFusedCtl* d_ctl = nullptr;
   BfsFusedCtl* h_ctl = nullptr;
@@ -1136,6 +1337,9 @@ struct BfsApp : gl_app {
     cudaFree(nz_in);
     cudaFree(gcol);
     cudaFree(hub_nbr_g);
+    cudaFree(ovgid_p);
+    cudaFree(dlg_list);
+    cudaFree(dlg_off);
     cudaFree(d_out8);
     cudaFree(deg8);
     if (ev_done) cudaEventDestroy(ev_done);
@@ -1177,7 +1381,7 @@ struct BfsApp : gl_app {
     g_col = fv.oe_col;
     g_nz = frag->nonzero_deg;
     // hub-first shadow graph (one fragment, undirected, large enough to matter)
-    if (fv.fnum == 1 && can_pull() && !fv.directed && fv.ivnum >= (1u << 16) && cfg.reserved[1] == 0) {
+    if (fv.fnum == 1 && can_pull() && !fv.directed && ((fv.ivnum >= (1u << 16) && cfg.reserved[1] == 0) || cfg.reserved[1] == 2)) {
       GL_TRY(build_hub_order(eng.stream, fv.oe_rp, fv.ivnum, &perm, &order));
       GL_TRY(build_permuted_csr(eng.stream, fv.oe_rp, fv.oe_col, frag->oe.entries, fv.ivnum, order, perm, &rp_p, &col_p));
       GL_CUDA(cudaMalloc(&nz_p, sizeof(uint32_t) * words));
@@ -1228,6 +1432,11 @@ struct BfsApp : gl_app {
       GL_TRY(mm.PeerAllReduce(eng.stream, &a, &b, &c, 0));
       g_m_total = (uint64_t) a;
       g_vnum = (uint64_t) b;
+      {
+        long long z = (long long) nz_total, z2 = 0;
+        GL_TRY(mm.PeerAllReduce(eng.stream, &z, &z2, &c, 0));
+        g_nz_total = (uint64_t) z;
+      }
       // every GPU must spill its level ring at the same depth
       long long lo = (long long) max_lv, dummy = 0;
       GL_TRY(mm.PeerAllReduce(eng.stream, &lo, &dummy, &c, 1));
@@ -1243,7 +1452,73 @@ struct BfsApp : gl_app {
       seg_stride = (seg_words + 63) & ~63u;
       seg_gens = (uint32_t) std::min<size_t>(32, seg_stride ? comm->mirror_bytes / ((size_t) seg_stride * 4) : 0);
       global_front = can_pull() && cfg.reserved[7] == 0 && seg_gens >= 2;
-      if (can_pull() && fv.ivnum + fv.ovnum) {
+      // Hub-first order inside every fragment (as on one GPU): inner lids become degree ranks, so the
+      // hot frontier / visited words are the first words of every segment, and the pull rows list the
+      // highest-ranked neighbours first.  Decided on facts every rank shares (the steps below are
+      // collective).  cfg.reserved[1] = 1 keeps the fragment's own order, 2 forces the hub-first
+      // one also on small graphs (tests).
+      hub_multi = global_front && fused() && !fv.directed &&
+                  ((cfg.reserved[1] == 0 && g_vnum >= (1u << 16)) || cfg.reserved[1] == 2 || cfg.reserved[1] == 3);
+      if (hub_multi) {
+        const uint64_t m = frag->oe.entries;
+        GL_TRY(build_hub_order(eng.stream, fv.oe_rp, fv.ivnum, &perm, &order));
+        GL_TRY(build_permuted_csr(eng.stream, fv.oe_rp, fv.oe_col, m, fv.ivnum, order, perm, &rp_p, &col_p, nullptr, nullptr, getenv("GL_HUB_SORT") ? atoi(getenv("GL_HUB_SORT")) != 0 : true));
+        GL_CUDA(cudaMalloc(&nz_p, sizeof(uint32_t) * words));
+        GL_CUDA(cudaMemsetAsync(nz_p, 0, sizeof(uint32_t) * words, eng.stream));
+        if (fv.ivnum) GL_LAUNCH(k_bfs_nz, (fv.ivnum + 255) / 256, 256, eng.stream, rp_p, fv.ivnum, nz_p);
+        g_rp = p_rp = rp_p;
+        g_col = p_col = col_p;
+        g_nz = nz_p;
+        if (deg8 && fv.ivnum) GL_LAUNCH(k_bfs_deg8, (fv.ivnum + 255) / 256, 256, eng.stream, g_rp, fv.ivnum, deg8);
+        if (has_src_) GL_CUDA(cudaMemcpy(&src_, perm + src_, 4, cudaMemcpyDeviceToHost));
+        // owners' new lids reach the outer copies through one dense mirror sync
+        uint32_t* newlid = nullptr;
+        GL_CUDA(cudaMalloc(&newlid, sizeof(uint32_t) * std::max<size_t>(tvnum, 1)));
+        GL_CUDA(cudaMemsetAsync(newlid, 0, sizeof(uint32_t) * std::max<size_t>(tvnum, 1), eng.stream));
+        if (fv.ivnum) GL_CUDA(cudaMemcpyAsync(newlid, perm, sizeof(uint32_t) * fv.ivnum, cudaMemcpyDeviceToDevice, eng.stream));
+        GL_TRY(mm.SyncValuesToGhosts(eng.stream, newlid, 4));
+        GL_CUDA(cudaMalloc(&ovgid_p, sizeof(uint32_t) * std::max<uint32_t>(fv.ovnum, 1)));
+        if (fv.ovnum)
+          GL_LAUNCH(k_bfs_ovgid_new, (fv.ovnum + 255) / 256, 256, eng.stream, fv.ovgid, newlid + fv.ivnum, fv.ovnum, fv.id_mask, ovgid_p);
+        const uint32_t gid0 = fv.fid << fv.fid_offset;
+        GL_CUDA(cudaMalloc(&gcol, sizeof(uint32_t) * (m + 16)));
+        GL_CUDA(cudaMalloc(&hub_nbr_g, sizeof(uint32_t) * ((size_t) fv.ivnum + kSuperV)));
+        GL_CUDA(cudaMemsetAsync(hub_nbr_g, 0xFF, sizeof(uint32_t) * ((size_t) fv.ivnum + kSuperV), eng.stream));
+        if (m) {
+          GL_LAUNCH(k_bfs_gcol, eng.sm_count * 8, 256, eng.stream, p_col, m, fv.ivnum, gid0, ovgid_p, gcol);
+          GL_LAUNCH(k_bfs_gid_key, eng.sm_count * 8, 256, eng.stream, gcol, m, fv.fid_offset, fv.id_mask, 1);
+          GL_TRY(sort_csr_rows(eng.stream, p_rp, fv.ivnum, m, &gcol));
+          GL_LAUNCH(k_bfs_gid_key, eng.sm_count * 8, 256, eng.stream, gcol, m, fv.fid_offset, fv.id_mask, 0);
+        }
+        // the first entry of a sorted row is its highest-ranked neighbour: the stage-1 probe of the pull
+        if (fv.ivnum) GL_LAUNCH(k_bfs_first_col, (fv.ivnum + 255) / 256, 256, eng.stream, p_rp, gcol, fv.ivnum, hub_nbr_g);
+        if (cfg.reserved[1] != 3) {   // ([1] = 3: hub-first order without the delegated hubs, A/B)
+          const uint32_t K = fv.fnum * kDlgPerFrag;
+          uint32_t* cnt = nullptr;
+          GL_CUDA(cudaMalloc(&cnt, sizeof(uint32_t) * K));
+          GL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * K, eng.stream));
+          if (fv.ivnum)
+            GL_LAUNCH(k_bfs_dlg_scan, (fv.ivnum + 255) / 256, 256, eng.stream, p_rp, gcol, fv.ivnum, fv.fid_offset, fv.id_mask, cnt,
+                      nullptr, nullptr, 0);
+          std::vector<uint32_t> h_cnt(K);
+          GL_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt, sizeof(uint32_t) * K, cudaMemcpyDeviceToHost, eng.stream));
+          GL_CUDA(cudaStreamSynchronize(eng.stream));
+          std::vector<uint64_t> h_off(K + 1, 0);
+          for (uint32_t h = 0; h < K; ++h) h_off[h + 1] = h_off[h] + h_cnt[h];
+          GL_CUDA(cudaMalloc(&dlg_off, sizeof(uint64_t) * (K + 1)));
+          GL_CUDA(cudaMemcpyAsync(dlg_off, h_off.data(), sizeof(uint64_t) * (K + 1), cudaMemcpyHostToDevice, eng.stream));
+          GL_CUDA(cudaMalloc(&dlg_list, sizeof(uint32_t) * (h_off[K] + 16)));
+          GL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * K, eng.stream));
+          if (fv.ivnum)
+            GL_LAUNCH(k_bfs_dlg_scan, (fv.ivnum + 255) / 256, 256, eng.stream, p_rp, gcol, fv.ivnum, fv.fid_offset, fv.id_mask, cnt,
+                      dlg_off, dlg_list, 1);
+          GL_TRY(sort_csr_rows(eng.stream, dlg_off, K, h_off[K], &dlg_list));   // ascending lid: neighbouring bits, neighbouring words
+          GL_CUDA(cudaStreamSynchronize(eng.stream));
+          cudaFree(cnt);
+        }
+        GL_CUDA(cudaStreamSynchronize(eng.stream));
+        cudaFree(newlid);
+      } else if (can_pull() && fv.ivnum + fv.ovnum) {
         // the hub-neighbour prefilter should pick the true highest-degree neighbour, also when it is an
         // outer copy: owners' degrees reach the ghosts through one dense mirror sync (collective)
         uint32_t* deg32 = nullptr;
@@ -1256,7 +1531,7 @@ struct BfsApp : gl_app {
       } else if (can_pull()) {
         GL_TRY(mm.SyncValuesToGhosts(eng.stream, nullptr, 4));   // keep the collective sequence identical on every rank
       }
-      if (global_front) {
+      if (global_front && !hub_multi) {
         const uint64_t m = (fv.directed ? frag->ie.entries : frag->oe.entries);
         const uint32_t gid0 = fv.fid << fv.fid_offset;
         GL_CUDA(cudaMalloc(&gcol, sizeof(uint32_t) * (m + 16)));
@@ -1367,9 +1642,12 @@ struct BfsApp : gl_app {
     if (multi) {
       ma.remote = remote;
       ma.ovnum = fv.ovnum;
-      ma.ovgid = fv.ovgid;
+      ma.ovgid = hub_multi ? ovgid_p : fv.ovgid;
       ma.g_m_total = g_m_total;
       ma.g_vnum = g_vnum;
+      ma.g_nz_total = g_nz_total;
+      ma.dlg_list = dlg_list;
+      ma.dlg_off = dlg_off;
       XComm& x = ma.x;
       x.fid = fv.fid;
       x.fnum = fv.fnum;
@@ -1389,6 +1667,7 @@ struct BfsApp : gl_app {
       x.my_words = (uint32_t) bm_words(fv.ivnum);
       x.seg_stride = seg_stride;
       x.seg_gens = seg_gens;
+      x.cta_fence = (getenv("GL_XSYNC_CTA_FENCE") && atoi(getenv("GL_XSYNC_CTA_FENCE"))) ? 1 : 0;
       if (global_front) {
         a.pa.col = gcol;
         a.pa.hub_nbr = hub_nbr_g;
@@ -1440,6 +1719,9 @@ struct BfsApp : gl_app {
       GL_LAUNCH(k_bfs_resume_prep, 1, 32, s, d_ctl);
     }
     if (multi) mm.bytes_sent += h_ctl->x_items * sizeof(ItemU32);
+    if (multi && getenv("GL_KTIME"))   // (not under GL_TRACE: its per-launch synchronisation distorts the gaps)
+      fprintf(stderr, "[gl-ktime] f%u seed end -> first instruction %.1f us, kernel %.1f us, levels %u\n", fv.fid,
+              (double) (h_ctl->t_kstart - h_ctl->t_begin) * 1e-3, (double) (h_ctl->t_kend - h_ctl->t_kstart) * 1e-3, h_ctl->levels);
     if (multi && trace_on()) {
       for (uint32_t l = 0; l < h_ctl->levels && l < 32; ++l) {
         const unsigned long long* t = h_ctl->ph[l];

@@ -341,6 +341,14 @@ GL_DEV void frontier_scan_phase(ScanSmem<typename Op::Meta>& sm,
   }
 }
 
+// Ops whose per-entry work is a bit set in a bitmap can take a whole warp's entries at once
+// (Op::kWarpEntries + Op::warp_edge): the hub phase then hands over 32 consecutive entries of the
+// row per call, all lanes converged.
+template <class Op, class = void>
+struct has_warp_entries : std::false_type {};
+template <class Op>
+struct has_warp_entries<Op, std::void_t<decltype(Op::kWarpEntries)>> : std::true_type {};
+
 // Hub phase: one work item = <= kHubChunk consecutive entries of one long row,
 // read with 128-bit coalesced loads.
 template <class Op>
@@ -360,6 +368,17 @@ GL_DEV void hub_scan_phase(uint32_t* s_item, EdgeRange er, const Op& op,
     HubItem h = hubs[it];
     auto meta = op.assign(h.v);
     uint64_t b = h.begin, e = h.end;
+    if constexpr (has_warp_entries<Op>::value) {
+      // warp w of the CTA takes entries [b + 32 w, b + 32 w + 32), then strides by the CTA width
+      for (uint64_t base = b + (threadIdx.x & ~31u); base < e; base += kTB) {
+        const uint64_t p = base + lane_id();
+        const bool valid = p < e;
+        const uint32_t v = valid ? ld_stream_u32(er.col + p) : 0u;
+        op.warp_edge(v, valid, acc);
+      }
+      if (threadIdx.x == 0) scanned += e - b;
+      continue;
+    }
     uint64_t ab = (b + 3) & ~3ull;
     if (ab > e) ab = e;
     uint64_t ae = ab + ((e - ab) & ~3ull);

@@ -131,4 +131,20 @@ int build_permuted_csr(cudaStream_t s, const uint64_t* rp, const uint32_t* col, 
   return GL_OK;
 }
 
+int sort_csr_rows(cudaStream_t s, const uint64_t* rp, uint32_t n, uint64_t m, uint32_t** col) {
+  if (!n || !m) return GL_OK;
+  uint32_t* sorted = nullptr;
+  GL_CUDA(cudaMalloc(&sorted, 4ull * (m + 16)));
+  size_t sb = 0;
+  void* st = nullptr;
+  GL_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, sb, *col, sorted, (int64_t) m, (int64_t) n, rp, rp + 1, s));
+  GL_CUDA(cudaMalloc(&st, std::max<size_t>(sb, 16)));
+  GL_CUDA(cub::DeviceSegmentedSort::SortKeys(st, sb, *col, sorted, (int64_t) m, (int64_t) n, rp, rp + 1, s));
+  GL_CUDA(cudaStreamSynchronize(s));
+  cudaFree(st);
+  cudaFree(*col);
+  *col = sorted;
+  return GL_OK;
+}
+
 }  // namespace gl

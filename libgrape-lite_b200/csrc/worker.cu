@@ -161,6 +161,11 @@ int gl_app_query(gl_app_t* a, gl_query_stats* stats) {
   GL_TRY(a->Init());  // context Init (gpu_worker.h:61): resets per-query state
   a->mm.Start();
   cudaStream_t s = a->eng.stream;
+  // run_cuda_app.h:117 puts an MPI_Barrier between Init and the timed Query.  Here the barrier is a
+  // device-side one on the query's stream: the GPUs' start events are then aligned to a few
+  // microseconds instead of the hosts' wake-up jitter (which the first in-kernel collective of a
+  // fused query would otherwise absorb inside the timed region).
+  if (a->fv.fnum > 1 && a->mm.use_peer_barrier && a->comm && a->comm->opened) GL_TRY(a->mm.PeerBarrierAsync(s));
   // --- the timed region of the reference: GPUWorker::Query (gpu_worker.h:69-107)
   GL_CUDA(cudaEventRecord(a->rec.next(), s));
   GL_TRY(a->mm.StartARound(s));
@@ -188,6 +193,7 @@ int gl_app_query(gl_app_t* a, gl_query_stats* stats) {
     float ms = 0;
     cudaEventElapsedTime(&ms, a->rec.ev[0], a->query_end ? a->query_end : a->rec.ev[a->rec.used - 1]);
     stats->query_ms = ms;
+    if (getenv("GL_KTIME")) fprintf(stderr, "[gl-ktime] query %.1f us (start event -> end event)\n", ms * 1e3);
     stats->entries_scanned = a->q_entries;
     stats->frontier_vertices = a->q_frontier;
     stats->touched_vertices = a->q_touched;

@@ -82,7 +82,7 @@ def main():
         mm.close()
         return out, rounds, total
 
-    for wmode, apps in ((0, ["bfs", "bfs_r1ship", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "wcc_opt", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp", "face2_sssp"])):
+    for wmode, apps in ((0, ["bfs", "bfs_hub", "bfs_hub_src2", "bfs_hub_nodlg", "bfs_nohub", "bfs_r1ship", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "wcc_opt", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp", "face2_sssp"])):
         n = 1 << scale
         frag = pkg.Fragment.rmat(scale, 16, seed=17, weight_mode=wmode, fid=rank, fnum=world)
         comm = gdist.make_comm(rank, world, frag.ivnum)
@@ -91,11 +91,14 @@ def main():
             src, dst, w = pkg.rmat_edges_host(scale, 16, 17, wmode)
             g = pyoracle.Graph(n, src, dst, None if w is None else w.astype(np.float64))
             source = g.max_degree_vertex()
+            # a second source that is NOT one of the highest-degree vertices (the delegated hubs)
+            deg = np.bincount(np.concatenate([src, dst]), minlength=n)
+            source2 = int(np.flatnonzero(deg == np.sort(deg[deg > 0])[len(deg[deg > 0]) // 2])[0])
         else:
-            source = 0
-        src_t = torch.tensor([source], dtype=torch.int64, device=dev)
+            source = source2 = 0
+        src_t = torch.tensor([source, source2], dtype=torch.int64, device=dev)
         dist.broadcast(src_t, 0)
-        source = int(src_t.item())
+        source, source2 = int(src_t[0].item()), int(src_t[1].item())
         only = os.environ.get("GL_APPS")
         if only:
             apps = [a for a in apps if a in only.split(",")]
@@ -110,6 +113,15 @@ def main():
                            fuse_supersteps=0 if name.endswith("_step") else 1)
                 if name == "bfs_r1ship":     # round-1 frontier shipment (per-holder bit-compressed slices)
                     cfg["reserved"] = {7: 1}
+                if name == "bfs_hub":        # hub-first relabelling inside every fragment, also on a small graph
+                    cfg["reserved"] = {1: 2}
+                if name == "bfs_hub_src2":   # hub-first order, source of median degree (not a delegated hub)
+                    cfg["reserved"] = {1: 2}
+                    cfg["source_oid"] = source2
+                if name == "bfs_hub_nodlg":  # hub-first order without the delegated-hub lists
+                    cfg["reserved"] = {1: 3}
+                if name == "bfs_nohub":      # the fragment's own vertex order
+                    cfg["reserved"] = {1: 1}
             elif name == "sssp":
                 cfg = dict(source_oid=source)
             elif name.startswith("pagerank"):
@@ -133,7 +145,7 @@ def main():
             got = gather(app.result())
             if rank == 0:
                 if kind == "bfs":
-                    ok = np.array_equal(got, g.bfs(source)[0])
+                    ok = np.array_equal(got, g.bfs(cfg["source_oid"])[0])
                 elif kind == "sssp":
                     ok = np.array_equal(got, g.sssp(source)[0])
                 elif kind in ("wcc", "wcc_opt"):
