@@ -205,11 +205,17 @@ def measure_app(G, pkg, frag, comm, kind, cfg, steps, warmup, flush, edges_fn, w
     extra_bytes = max(0, free0 - G.free_bytes())
     pinned = pkg.PinnedBuffer(8 * max(frag.ivnum, 1))
     out = pinned.array(pkg.capi.RESULT_DTYPE[app.kind], frag.ivnum)
-    for _ in range(max(warmup, 1)):
-        st = app.query()
+    st = app.query()
     res = app.result(out).copy()
     edges = edges_fn(res)
     G.barrier()
+    # warm-up steps in the cadence of the timed ones (flush, barrier, query) and directly in front of them:
+    # a pause between warm-up and timed region (result copy, edge count) lets the NVLink links and the
+    # clocks fall back to their idle state, and the first timed multi-GPU query then paid ~190 us for it
+    for _ in range(max(warmup, 1)):
+        flush.zero_()
+        G.barrier()
+        st = app.query()
     t_dev, launches, stats = 0.0, 0, []
     for _ in range(steps):
         flush.zero_()                      # L2 flush between timed iterations

@@ -390,27 +390,60 @@ GL_DEV bool bfs_pull_phase(PullSmem& sm, const PullArgs& a,
       }
       __syncthreads();
       const uint32_t nc = (total - base) < (uint32_t) kTileV ? (total - base) : (uint32_t) kTileV;
-      // 2a: every thread probes at most kPullSerialCap entries of its rows;
-      // longer rows go to the warp-cooperative pass so that one unlucky
-      // thread cannot stall the CTA behind a chain of dependent loads
-      for (uint32_t i = threadIdx.x; i < nc; i += kTB) {
-        const uint32_t v = sm.v[i];
-        const uint64_t b = a.rp[v];
-        const uint32_t len = (uint32_t) (a.row_end[v] - b);
-        const uint32_t* row = a.col + b;
-        const uint32_t lim = len < kPullSerialCap ? len : kPullSerialCap;
-        bool found = false;
-        uint32_t p = 0;
-        for (; p < lim; ++p) {
-          if (front_test<kGlobal>(a, cur, row[p])) {
-            found = true;
-            ++p;
-            break;
+      // 2a: every thread probes at most kPullSerialCap entries of its (up to kTileV / kTB = 4) rows;
+      // longer rows go to the warp-cooperative pass so that one unlucky thread cannot stall the
+      // CTA behind a chain of dependent loads.  The four rows are walked in lock step: their
+      // row-pointer reads, column reads and frontier probes are four independent chains in flight
+      // (one after the other, a ticket of leftovers cost 4 x (2 + 2 probes) dependent latencies per
+      // thread, and the level ended with CTAs waiting tens of microseconds for the last tickets).
+      constexpr int kRows = kTileV / kTB;
+      static_assert(kRows == 4, "stage 2a is written for four candidates per thread");
+      // (the several-fragment probe keeps more state live: two rows at a time there, else spills)
+      constexpr int kIL = kGlobal ? 2 : 4;
+      const uint32_t dummy = kGlobal ? a.hub_dummy : 0u;
+#pragma unroll 1
+      for (int g = 0; g < kRows; g += kIL) {
+        uint32_t vv[kIL], len[kIL];
+        uint64_t bb[kIL];
+#pragma unroll
+        for (int k = 0; k < kIL; ++k) {
+          const uint32_t i = threadIdx.x + (g + k) * kTB;
+          vv[k] = i < nc ? sm.v[i] : kInfU32;
+        }
+#pragma unroll
+        for (int k = 0; k < kIL; ++k) bb[k] = vv[k] != kInfU32 ? a.rp[vv[k]] : 0ull;
+        uint32_t act = 0, foundm = 0;
+#pragma unroll
+        for (int k = 0; k < kIL; ++k) {
+          len[k] = vv[k] != kInfU32 ? (uint32_t) (a.row_end[vv[k]] - bb[k]) : 0u;
+          if (len[k]) act |= 1u << k;
+        }
+        for (uint32_t p = 0; p < kPullSerialCap && act; ++p) {
+          uint32_t ids[kIL];
+#pragma unroll
+          for (int k = 0; k < kIL; ++k) ids[k] = ((act >> k) & 1u) ? a.col[bb[k] + p] : dummy;
+          bool t[kIL];
+#pragma unroll
+          for (int k = 0; k < kIL; ++k) t[k] = front_test<kGlobal>(a, cur, ids[k]);   // unconditional: all in flight
+          scanned += __popc(act);
+#pragma unroll
+          for (int k = 0; k < kIL; ++k) {
+            if ((act >> k) & 1u) {
+              if (t[k]) {
+                foundm |= 1u << k;
+                act &= ~(1u << k);
+              } else if (p + 1 >= len[k]) {
+                act &= ~(1u << k);
+              }
+            }
           }
         }
-        scanned += p;
-        if (found) atomicOr(&sm.words[(v >> 5) - st * (kSuperV / 32)], 1u << (v & 31));
-        else if (len > kPullSerialCap) sm.lng[atomicAdd(&sm.nlong, 1u)] = v;
+#pragma unroll
+        for (int k = 0; k < kIL; ++k) {
+          if (vv[k] == kInfU32) continue;
+          if ((foundm >> k) & 1u) atomicOr(&sm.words[(vv[k] >> 5) - st * (kSuperV / 32)], 1u << (vv[k] & 31));
+          else if (len[k] > kPullSerialCap) sm.lng[atomicAdd(&sm.nlong, 1u)] = vv[k];
+        }
       }
       __syncthreads();
       // 2b: one warp per long row, 32 entries per step
@@ -919,15 +952,26 @@ GL_DEV bool front_ship(const XComm& x, uint32_t par, uint32_t off, const uint32_
   }
   return wrote;
 }
-// the segments of parity `par` were consumed: back to zero for their next use (two shipments later)
+// the segments of parity `par` were consumed: back to zero for their next use.  16-byte loads, four
+// segments' loads in flight per thread (one word per iteration made this a chain of ~30 dependent
+// L2 latencies per level at eight fragments).
 GL_DEV void front_zero(const XComm& x, uint32_t par, uint32_t off) {
   const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
   const uint64_t gtid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t total = (uint64_t) x.fnum * x.seg_words;
-  for (uint64_t i = gtid; i < total; i += nthreads) {
-    const uint32_t f = (uint32_t) (i / x.seg_words), w = (uint32_t) (i % x.seg_words);
-    uint32_t* seg = (uint32_t*) x.mrecv[par][f] + off;
-    if (__ldcg(seg + w)) seg[w] = 0u;
+  const uint32_t n4 = x.seg_stride >> 2;   // a generation is seg_stride words (multiple of 64), zero-padded
+  for (uint64_t i = gtid; i < n4; i += nthreads) {
+    for (uint32_t f0 = 0; f0 < x.fnum; f0 += 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (f0 + k < x.fnum) v[k] = __ldcg((const uint4*) ((const uint32_t*) x.mrecv[par][f0 + k] + off) + i);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (v[k].x | v[k].y | v[k].z | v[k].w)
+          ((uint4*) ((uint32_t*) x.mrecv[par][f0 + k] + off))[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 }
 
