@@ -538,6 +538,7 @@ struct BfsFusedCtl {
   unsigned long long x_items;   // items this GPU sent
   unsigned long long ph[32][6];
   unsigned long long xw[32][2];  // GL_TRACE: per level: peer wait / first grid.sync of its last xsync
+  unsigned long long l_nf;               // several fragments: this fragment's part of the current frontier (statistics)
   unsigned long long r_visited_cnt_g;    // several fragments: vertices visited so far in the whole graph (resume state)
   unsigned long long t_kstart, t_kend;   // GL_TRACE: first / last instruction of the fused multi-fragment kernel (thread 0)
   unsigned long long xt[8];      // GL_TRACE: timestamps inside the most recent xsync (block 0, thread 0)   // GL_TRACE: phase timestamps of the first 32 levels (thread 0)
@@ -1040,11 +1041,13 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
     m_f = (unsigned long long) S[1];
     visited_edges = m_f;
     visited_cnt = n_f;
+    if (gtid == 0) ctl->l_nf = ctl->r_nf;   // this fragment's part of the current frontier (statistics)
     phase = 0;
   } else {
     n_f = ctl->r_nf;
     m_f = ctl->r_mf;
     visited_edges = ctl->r_visited_edges;
+    if (gtid == 0) ctl->l_nf = n_f / x.fnum;   // resumed after a ring spill: the share is not carried over
   }
   for (uint32_t depth = 0; n_f != 0; ++depth) {
     if (depth + 1 >= a.max_lv) {
@@ -1252,10 +1255,14 @@ __global__ void __launch_bounds__(kTB, GL_BFS_FUSED_CTAS) k_bfs_fused_multi(BfsM
         BfsLevelStat ls;
         ls.t_ns = global_ns();
         ls.scanned = VC->scanned;
-        ls.frontier = (uint32_t) (n_f > 0xFFFFFFFFull ? 0xFFFFFFFFull : n_f);
+        // THIS fragment's share of the level's frontier (n_f is the whole graph's): what it found in the
+        // previous level (vertices that arrived as messages in a push level are not counted)
+        const unsigned long long l_nf = ctl->l_nf;
+        ls.frontier = (uint32_t) (l_nf > 0xFFFFFFFFull ? 0xFFFFFFFFull : l_nf);
         ls.mode = phase == 1 ? 1u : 0u;
         ctl->stat[adepth] = ls;
       }
+      ctl->l_nf = VC->next_count;
       ctl->levels = adepth + 1;
       ctl->touched += VC->touched;
       ctl->c[(depth + 2) % 3] = ScanCtrl();
