@@ -446,7 +446,13 @@ typedef struct {
 } gl_query_stats;
 
 /* GPUWorker::Query: PEval then IncEval until every fragment is idle
- * (gpu_worker.h:69-107). Asynchronous work is finished when it returns. */
+ * (gpu_worker.h:69-107). Asynchronous work is finished when it returns.
+ * Collective on a fragment group: every rank calls it for the same query.  With
+ * an opened communicator the call first meets the other ranks in a device-side
+ * barrier on the app's stream (the MPI_Barrier in front of the reference's timed
+ * Query(), run_cuda_app.h:117); query_ms starts after it.
+ * step_frontier[] of a several-fragment fused BFS is THIS fragment's share of
+ * each level's frontier. */
 int gl_app_query(gl_app_t*, gl_query_stats* stats /* may be NULL */);
 /* Context::Output values for the inner vertices, in lid order, to HOST memory
  * (e.g. cuda/sssp/sssp.h:104-118).  elem: see gl_app_kind. */

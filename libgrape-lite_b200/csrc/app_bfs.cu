@@ -1513,7 +1513,7 @@ struct BfsApp : gl_app {
       if (hub_multi) {
         const uint64_t m = frag->oe.entries;
         GL_TRY(build_hub_order(eng.stream, fv.oe_rp, fv.ivnum, &perm, &order));
-        GL_TRY(build_permuted_csr(eng.stream, fv.oe_rp, fv.oe_col, m, fv.ivnum, order, perm, &rp_p, &col_p, nullptr, nullptr, getenv("GL_HUB_SORT") ? atoi(getenv("GL_HUB_SORT")) != 0 : true));
+        GL_TRY(build_permuted_csr(eng.stream, fv.oe_rp, fv.oe_col, m, fv.ivnum, order, perm, &rp_p, &col_p));
         GL_CUDA(cudaMalloc(&nz_p, sizeof(uint32_t) * words));
         GL_CUDA(cudaMemsetAsync(nz_p, 0, sizeof(uint32_t) * words, eng.stream));
         if (fv.ivnum) GL_LAUNCH(k_bfs_nz, (fv.ivnum + 255) / 256, 256, eng.stream, rp_p, fv.ivnum, nz_p);
