@@ -82,7 +82,7 @@ def main():
         mm.close()
         return out, rounds, total
 
-    for wmode, apps in ((0, ["bfs", "bfs_hub", "bfs_hub_src2", "bfs_hub_nodlg", "bfs_nohub", "bfs_r1ship", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "wcc_opt", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp", "face2_sssp"])):
+    for wmode, apps in ((0, ["bfs", "bfs_hub", "bfs_hub_src2", "bfs_hub_nodlg", "bfs_spill", "bfs_spill_src2", "bfs_nohub", "bfs_r1ship", "bfs_push", "bfs_step", "bfs_push_step", "wcc", "wcc_opt", "pagerank", "pagerank_pull", "cdlp", "lcc"]), (1, ["sssp", "face2_sssp"])):
         n = 1 << scale
         frag = pkg.Fragment.rmat(scale, 16, seed=17, weight_mode=wmode, fid=rank, fnum=world)
         comm = gdist.make_comm(rank, world, frag.ivnum)
@@ -120,6 +120,11 @@ def main():
                     cfg["source_oid"] = source2
                 if name == "bfs_hub_nodlg":  # hub-first order without the delegated-hub lists
                     cfg["reserved"] = {1: 3}
+                if name == "bfs_spill":      # a ring of 4 level bitmaps: the fused kernel parks, the host spills, relaunch
+                    cfg["reserved"] = {1: 2, 3: 4}
+                if name == "bfs_spill_src2":
+                    cfg["reserved"] = {1: 1, 3: 4}
+                    cfg["source_oid"] = source2
                 if name == "bfs_nohub":      # the fragment's own vertex order
                     cfg["reserved"] = {1: 1}
             elif name == "sssp":
