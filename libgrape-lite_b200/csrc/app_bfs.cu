@@ -1766,6 +1766,12 @@ struct BfsApp : gl_app {
       }
       if (!h_ctl->overflow) break;
       // deeper than the ring: spill and resume (high-diameter graphs)
+      // A launch that parks right after a pull level leaves that level's shipment unconsumed in its
+      // frontier generation.  Within THIS query the stale bits are harmless (every neighbour of an
+      // already expanded frontier vertex is visited), but they must not survive into another query
+      // on this communicator: the next Init re-zeroes the segments (collective; all ranks spill at
+      // the same depth, so all of them set the flag).
+      if (multi && global_front) comm->mirror_dirty = true;
       GL_TRY(SpillRing());
       GL_LAUNCH(k_bfs_resume_prep, 1, 32, s, d_ctl);
     }
