@@ -26,7 +26,7 @@ def test_distributed_protocol_model(nproc):
 def test_reference_arm_under_torchrun_rank0_only():
     """--impl reference: rank 0 alone runs and prints ONE json line; other ranks exit 0."""
     p = _torchrun(2, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
-                  "--warmup", "1", "--cpu-scale", "12", port=29631)   # 3 queries in one reference process
+                  "--warmup", "1", "--ref-scale", "12", port=29631)   # 3 queries in one reference process
     assert p.returncode == 0, p.stdout[-3000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
